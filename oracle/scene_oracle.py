@@ -1,0 +1,293 @@
+"""CPU oracle for the six-camera scene pipeline -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (driving-dirty_b200/) never imports it and fails
+loudly when its CUDA library is missing.
+
+What it is: a restatement of the reference's algorithm for the hot path as plain functions
+over a flat ``params`` dict (keys = the reference's state_dict keys).  The reference is a
+Python/PyTorch program whose arithmetic is torch's CPU ops, so the floating-point pieces are
+restated with the same torch CPU primitives (conv2d, linear, batch_norm, ...) composed by
+hand; the byte/index pieces (stitch, flat max-pool, binarise, threat-score counts) are
+restated in numpy integer/index arithmetic and, again, in C (oracle/scene_oracle.c).
+
+Parity pinning: the reference ships no tests or golden vectors.  The
+oracle is pinned against outputs of the UNMODIFIED reference modules imported from
+/root/reference in the build container (oracle/make_golden.py, dependency shims under
+oracle/shims/); those outputs are committed under tests/golden/ and tests/test_oracle.py
+checks the oracle against them bit-for-bit.
+
+Every function cites the reference lines it follows (paths relative to /root/reference/src).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+VIEW_ORDER = (0, 1, 2, 5, 4, 3)  # roadmap_bce_v2.py:58, autoencoder.py:55, spatial_w_rm.py:58
+BINARISE_THRESHOLD_BITS = 0x33C00000  # sigmoid(x).round()==1  <=>  x > 1.5*2**-24 (see binarise)
+
+
+# ----------------------------------------------------------------------------------------
+# A1 / A2: stitch
+# ----------------------------------------------------------------------------------------
+def stitch(views: torch.Tensor) -> torch.Tensor:
+    """mosaic[b,c,h,j*W+w] = views[b,VIEW_ORDER[j],c,h,w].
+
+    roadmap_bce_v2.py:53-64 (wide_stitch_six_images): stack, x[:, [0,1,2,5,4,3]],
+    permute(0,2,3,1,4).reshape(b,c,h,-1).  Restated as an explicit index gather in numpy.
+    """
+    v = views.detach().cpu().numpy()
+    b, n, c, h, w = v.shape
+    assert n == 6
+    out = np.empty((b, c, h, 6 * w), dtype=v.dtype)
+    for j, src in enumerate(VIEW_ORDER):
+        out[:, :, :, j * w:(j + 1) * w] = v[:, src]
+    return torch.from_numpy(out)
+
+
+def six_to_one(views: torch.Tensor, target_slot: int):
+    """autoencoder.py:53-73 (six_to_one_task) with the host RNG draw made explicit.
+
+    The reference draws ``target_slot = np.random.randint(0, 5)`` (slot 5 never chosen),
+    clones mosaic[..., 306t:306t+306] as y and zeroes that block of x.  The slot width is the
+    view width (306 in the reference; parametrised here for reduced-geometry tests).
+    """
+    x = stitch(views).clone()
+    w = views.shape[-1]
+    s, e = target_slot * w, (target_slot + 1) * w
+    y = x[:, :, :, s:e].clone()
+    x[:, :, :, s:e] = 0.0
+    return x, y
+
+
+# ----------------------------------------------------------------------------------------
+# A3 / A4 / A5: encoder convs and the flat max-pool
+# ----------------------------------------------------------------------------------------
+def encoder_convs(p: dict, x: torch.Tensor, prefix: str = "ae.encoder."):
+    """components.py:41-43: relu(c1), relu(c2), relu(c3 stride 2), all 3x3 pad 1."""
+    a1 = F.relu(F.conv2d(x, p[prefix + "c1.weight"], p[prefix + "c1.bias"], padding=1))
+    a2 = F.relu(F.conv2d(a1, p[prefix + "c2.weight"], p[prefix + "c2.bias"], padding=1))
+    a3 = F.relu(F.conv2d(a2, p[prefix + "c3.weight"], p[prefix + "c3.bias"], stride=2, padding=1))
+    return a1, a2, a3
+
+
+def pool4_flat(a3: torch.Tensor) -> torch.Tensor:
+    """components.py:46-47: view(B,-1) then max_pool1d(kernel_size=4) over the NCHW-flat index.
+
+    numpy restatement: reshape to [B, n/4, 4] and take the max; the trailing n%4 elements are
+    dropped exactly as max_pool1d (floor mode) drops them.
+    """
+    v = a3.detach().cpu().numpy().reshape(a3.shape[0], -1)
+    n = v.shape[1] // 4
+    return torch.from_numpy(v[:, :n * 4].reshape(v.shape[0], n, 4).max(axis=2).copy())
+
+
+def pool4_flat_argmax(a3: torch.Tensor) -> np.ndarray:
+    """First-max index inside each window (torch's max_pool backward routes to the first max)."""
+    v = a3.detach().cpu().numpy().reshape(a3.shape[0], -1)
+    n = v.shape[1] // 4
+    return v[:, :n * 4].reshape(v.shape[0], n, 4).argmax(axis=2).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------------------
+# A6 / A7: DenseBlock with the always-on dropout
+# ----------------------------------------------------------------------------------------
+def dense_block(p: dict, prefix: str, x: torch.Tensor, training: bool, drop_p: float = 0.2,
+                momentum: float = 0.1, eps: float = 1e-5) -> torch.Tensor:
+    """components.py:104-109: Linear -> BatchNorm1d -> ReLU -> F.dropout(x, p) (training=True
+    default: NEVER disabled).  BatchNorm uses batch statistics and updates the
+    running buffers in ``p`` in place when ``training`` (i.e. after unfreeze()).
+    """
+    y = F.linear(x, p[prefix + "fc1.weight"], p[prefix + "fc1.bias"])
+    y = F.batch_norm(y, p[prefix + "fc_bn.running_mean"], p[prefix + "fc_bn.running_var"],
+                     p[prefix + "fc_bn.weight"], p[prefix + "fc_bn.bias"],
+                     training=training, momentum=momentum, eps=eps)
+    if training and (prefix + "fc_bn.num_batches_tracked") in p:
+        p[prefix + "fc_bn.num_batches_tracked"] += 1
+    y = F.relu(y)
+    return F.dropout(y, drop_p)  # consumes the global torch RNG exactly like the reference
+
+
+def encoder_forward(p: dict, x: torch.Tensor, training: bool, prefix: str = "ae.encoder.",
+                    c3_only: bool = False) -> torch.Tensor:
+    """components.py:40-52 (Encoder.forward)."""
+    _, _, a3 = encoder_convs(p, x, prefix)
+    if c3_only:  # components.py:44-45
+        return a3
+    # components.py:46-47.  F.max_pool1d (not amax) so that autograd routes the gradient to the
+    # FIRST maximum of each window like the reference; pool4_flat() above is the index-level
+    # restatement and tests check the two agree.
+    pooled = F.max_pool1d(a3.reshape(a3.shape[0], -1).unsqueeze(1), kernel_size=4).squeeze(1)
+    h = dense_block(p, prefix + "fc1.", pooled, training)
+    h = dense_block(p, prefix + "fc2.", h, training)
+    return F.linear(h, p[prefix + "fc_z_out.weight"], p[prefix + "fc_z_out.bias"])
+
+
+# ----------------------------------------------------------------------------------------
+# A8-A11: roadmap head, loss, binarise, threat score
+# ----------------------------------------------------------------------------------------
+def roadmap_forward(p: dict, views, training: bool, map_hw: int = 800):
+    """roadmap_bce_v2.py:66-81: stitch -> encoder -> Linear(latent, 800*800) -> reshape;
+    returns (logits, sigmoid(logits)).  ``views`` may be a [B,6,3,H,W] tensor or the
+    collate_fn tuple of [6,3,H,W] tensors (roadmap_bce_v2.py:55 stacks it)."""
+    if not torch.is_tensor(views):
+        views = torch.stack(tuple(views), dim=0)
+    x = stitch(views)
+    z = encoder_forward(p, x, training)
+    y = F.linear(z, p["fc1.weight"], p["fc1.bias"]).reshape(z.shape[0], map_hw, map_hw)
+    return y, torch.sigmoid(y)
+
+
+def bce_with_logits_mean(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """roadmap_bce_v2.py:103-106: F.binary_cross_entropy_with_logits on [B, H*W] views, mean
+    over B*H*W.  Elementwise form: (1-t)*x + max(-x,0) + log1p(exp(-|x|)); float64 sum."""
+    x = logits.detach().double().reshape(-1)
+    t = target.detach().double().reshape(-1)
+    per = (1.0 - t) * x + torch.clamp(-x, min=0.0) + torch.log1p(torch.exp(-x.abs()))
+    return (per.sum() / x.numel()).float()
+
+
+def bce_with_logits_grad(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """d(mean BCE)/d logits = (sigmoid(x) - t) / numel  (SURVEY A9)."""
+    return (torch.sigmoid(logits) - target) / logits.numel()
+
+
+def binarise(probs_or_logits: torch.Tensor, from_logits: bool = False) -> torch.Tensor:
+    """roadmap_bce_v2.py:140 / :115: ``probs.round()`` (round-half-even of the fp32 sigmoid).
+
+    From logits this equals ``x > 1.5 * 2**-24`` bit-for-bit: an exhaustive sweep of every
+    fp32 in [2**-27, 2**-20) through torch's CPU sigmoid (tests/test_oracle.py repeats it)
+    shows sigmoid(x).round() flips 0 -> 1 exactly between 0x33C00000 and 0x33C00001 and is
+    monotone either side; sigmoid(0)=0.5 rounds (half to even) to 0.
+    """
+    if from_logits:
+        thr = np.uint32(BINARISE_THRESHOLD_BITS).view(np.float32)
+        return (probs_or_logits > float(thr)).to(torch.float32)
+    return probs_or_logits.round()
+
+
+def threat_score(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """helper.py:74-77: tp = (a*b).sum(); tp*1.0 / (a.sum() + b.sum() - tp), fp32, pooled
+    over the whole batch.  Restated with torch fp32 sums (same reduction as the reference)."""
+    tp = (a * b).sum()
+    return tp * 1.0 / (a.sum() + b.sum() - tp)
+
+
+def threat_score_counts(target01: torch.Tensor, pred01: torch.Tensor):
+    """Integer restatement for 0/1 maps: returns (tp, n_target, n_pred) as python ints.
+    TS = tp / (n_target + n_pred - tp).  Exact for any batch size (the reference's fp32 sums
+    are exact only while every partial < 2**24, i.e. <= 26 scenes -- SURVEY H5)."""
+    t = target01.detach().cpu().numpy().astype(np.int64).reshape(-1)
+    r = pred01.detach().cpu().numpy().astype(np.int64).reshape(-1)
+    return int((t * r).sum()), int(t.sum()), int(r.sum())
+
+
+def run_step(p: dict, views, road_image, training: bool, seed: int | None = None):
+    """roadmap_bce_v2.py:83-108 (_run_step) + :135-143 (validation_step metrics).
+
+    Returns dict(loss, logits, probs, ts, ts_rounded).  ``seed`` re-seeds the torch RNG just
+    before the forward so that the always-on dropout mask is reproducible.
+    """
+    if not torch.is_tensor(road_image):
+        road_image = torch.stack(tuple(road_image), dim=0)
+    target = road_image.float()  # :87
+    if seed is not None:
+        torch.manual_seed(seed)
+    logits, probs = roadmap_forward(p, views, training, map_hw=target.shape[-1])
+    b = target.shape[0]
+    loss = F.binary_cross_entropy_with_logits(logits.view(b, -1), target.view(b, -1))  # :106
+    return dict(loss=loss, logits=logits, probs=probs, target=target,
+                ts=threat_score(target, probs), ts_rounded=threat_score(target, probs.round()))
+
+
+def train_step_grads(p: dict, views, road_image, seed: int, names=None):
+    """fwd + BCE + backward through the restated path with torch autograd on CPU (what
+    loss.backward() does in the reference after unfreeze(), roadmap_bce_v2.py:125-133).
+    Returns (out dict, {name: grad})."""
+    names = names or [k for k, v in p.items() if v.is_floating_point()
+                      and not k.endswith(("running_mean", "running_var"))]
+    q = dict(p)
+    for k in names:
+        q[k] = p[k].detach().clone().requires_grad_(True)
+    for k in p:
+        if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+            q[k] = p[k].clone()
+    out = run_step(q, views, road_image, training=True, seed=seed)
+    out["loss"].backward()
+    return out, {k: q[k].grad for k in names}
+
+
+# ----------------------------------------------------------------------------------------
+# A13 / A14: AE decoder and MSE (config 3)
+# ----------------------------------------------------------------------------------------
+def decoder_forward(p: dict, z: torch.Tensor, training: bool, hw, prefix: str = "decoder."):
+    """components.py:85-93 (Decoder.forward); hw = (deconv_dim_h, deconv_dim_w)."""
+    x = dense_block(p, prefix + "fc1.", z, training)
+    x = dense_block(p, prefix + "fc2.", x, training)
+    x = x.view(x.size(0), 64, hw[0], hw[1])
+    x = F.relu(F.conv_transpose2d(x, p[prefix + "dc1.weight"], p[prefix + "dc1.bias"], padding=1))
+    x = F.relu(F.conv_transpose2d(x, p[prefix + "dc2.weight"], p[prefix + "dc2.bias"], padding=1))
+    x = F.relu(F.conv_transpose2d(x, p[prefix + "dc3.weight"], p[prefix + "dc3.bias"], stride=2))
+    return F.conv_transpose2d(x, p[prefix + "dc4.weight"], p[prefix + "dc4.bias"])
+
+
+def ae_run_step(p: dict, views: torch.Tensor, target_slot: int, training: bool, hw,
+                seed: int | None = None):
+    """autoencoder.py:78-93: six_to_one_task -> encoder -> decoder -> F.mse_loss(y, y_hat)."""
+    x, y = six_to_one(views, target_slot)
+    if seed is not None:
+        torch.manual_seed(seed)
+    z = encoder_forward(p, x, training, prefix="encoder.")
+    y_hat = decoder_forward(p, z, training, hw)
+    return dict(loss=F.mse_loss(y, y_hat), x=x, y=y, z=z, y_hat=y_hat)
+
+
+def strided_sample(t: torch.Tensor, n: int = 4096) -> torch.Tensor:
+    """n evenly spaced elements of the flattened tensor (integer index arithmetic); how the
+    golden files keep a checkable slice of tensors too large to commit."""
+    f = t.detach().reshape(-1)
+    idx = (torch.arange(n, dtype=torch.int64) * (f.numel() - 1)) // max(n - 1, 1)
+    return f[idx.to(f.device)].clone()
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic inputs / weights shared by tests, smoke() and bench.py
+# ----------------------------------------------------------------------------------------
+def synthetic_scene_batch(batch: int, view_h: int = 256, view_w: int = 306, map_hw: int = 800,
+                          seed: int = 20200505):
+    g = torch.Generator().manual_seed(seed)
+    views = torch.rand(batch, 6, 3, view_h, view_w, generator=g)
+    road = torch.rand(batch, map_hw, map_hw, generator=g) > 0.5
+    return views, road
+
+
+def init_roadmap_params(hidden: int, latent: int, view_h: int, view_w: int, map_hw: int = 800,
+                        seed: int = 20200505) -> dict:
+    """Random-init parameters with the reference's shapes and torch default initialisers
+    (nn.Conv2d / nn.Linear kaiming-uniform(a=sqrt(5)), BatchNorm1d ones/zeros), keyed like
+    RoadMapBCE.state_dict() after ``self.ae.decoder = None`` (roadmap_bce_v2.py:43-50)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def uni(shape, fan_in):
+        bound = 1.0 / fan_in ** 0.5
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+    mh, mw = view_h, 6 * view_w
+    h3, w3 = (mh - 1) // 2 + 1, (mw - 1) // 2 + 1
+    pooled = (32 * h3 * w3) // 4
+    p = {}
+    e = "ae.encoder."
+    p[e + "c1.weight"], p[e + "c1.bias"] = uni((32, 3, 3, 3), 27), uni((32,), 27)
+    p[e + "c2.weight"], p[e + "c2.bias"] = uni((32, 32, 3, 3), 288), uni((32,), 288)
+    p[e + "c3.weight"], p[e + "c3.bias"] = uni((32, 32, 3, 3), 288), uni((32,), 288)
+    for name, (i, o) in (("fc1.", (pooled, hidden)), ("fc2.", (hidden, hidden))):
+        p[e + name + "fc1.weight"], p[e + name + "fc1.bias"] = uni((o, i), i), uni((o,), i)
+        p[e + name + "fc_bn.weight"], p[e + name + "fc_bn.bias"] = torch.ones(o), torch.zeros(o)
+        p[e + name + "fc_bn.running_mean"] = torch.zeros(o)
+        p[e + name + "fc_bn.running_var"] = torch.ones(o)
+        p[e + name + "fc_bn.num_batches_tracked"] = torch.tensor(0)
+    p[e + "fc_z_out.weight"], p[e + "fc_z_out.bias"] = uni((latent, hidden), hidden), uni((latent,), hidden)
+    p["fc1.weight"], p["fc1.bias"] = uni((map_hw * map_hw, latent), latent), uni((map_hw * map_hw,), latent)
+    return p
