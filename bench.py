@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- 6-view scenes/sec of the RoadMapBCE training step on B200 (BASELINE.json config 2:
+bf16 activations, batch 32 scenes per GPU, views 6x3x256x306, hidden 256 / latent 128).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+One "step" = zero_grad + stitch/conv encoder/dense blocks/800x800 head + fused BCE/threat score +
+backward + (N>1: gradient all-reduce) + Adam, on one batch of synthetic scenes.  `value` is timed
+on the device with inputs resident in HBM; `e2e` goes through the reference-facing module call with
+HOST (pinned) input buffers, H2D copies and a D2H read of the loss inside the timed region.
+`--impl reference` times the CPU port of the reference path (oracle/scene_oracle.py: the same torch
+CPU ops the reference executes; /root/reference itself is not present on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "6-view scenes/sec, RoadMapBCE train step (fwd + BCE/threat-score + bwd + Adam)"
+UNIT = "scenes/s"
+VIEW_H, VIEW_W, MAP = 256, 306, 800
+HIDDEN, LATENT = 256, 128
+FLOP_C2_PER_SCENE = 2.0 * 256 * 1836 * 32 * 288      # 8.663 GFLOP
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="scenes per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path
+# ------------------------------------------------------------------------------------------------
+def cpu_train_steps(batch: int, steps: int, warmup: int):
+    """fwd + BCE + TS + backward + Adam of the reference path on the host cores (torch CPU ops =
+    what the reference executes), B=`batch` scenes per step.  Returns (scenes/s, seconds/step)."""
+    from oracle import scene_oracle as so
+    torch.set_num_threads(os.cpu_count())
+    params = so.init_roadmap_params(HIDDEN, LATENT, VIEW_H, VIEW_W)
+    views, road = so.synthetic_scene_batch(batch, VIEW_H, VIEW_W)
+    names = [k for k, v in params.items() if v.is_floating_point() and "running_" not in k]
+    leaves = {k: params[k].clone().requires_grad_(True) for k in names}
+    opt = torch.optim.Adam(list(leaves.values()), lr=1e-3)
+    p = dict(params)
+    p.update(leaves)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = so.run_step(p, views, road, training=True, seed=1234 + i)
+        out["loss"].backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = statistics.median(times)
+    return batch / sec, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    sps, sec = cpu_train_steps(args.cpu_batch, steps, warm)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RoadMapBCE train step, views 6x3x{VIEW_H}x{VIEW_W}, hidden {HIDDEN} latent {LATENT}, "
+                               f"map {MAP}x{MAP}; CPU sample = {args.cpu_batch} scenes/step"},
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of B={args.cpu_batch} scenes (fwd+BCE+TS+bwd+Adam), torch CPU ops, "
+                                   f"{cores} threads"},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def build_model(dtype: str, device):
+    from tests.helpers import make_roadmap_model
+    from oracle import scene_oracle as so   # only for the deterministic synthetic weights / scenes
+    params = so.init_roadmap_params(HIDDEN, LATENT, VIEW_H, VIEW_W)
+    model = make_roadmap_model(params, HIDDEN, LATENT, VIEW_H, VIEW_W, dtype=dtype, device=device)
+    model.frozen = False
+    model.ae.unfreeze()
+    model.train()
+    return model
+
+
+def time_kernel(fn, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def dominant_kernel_roofline(batch: int, dtype: torch.dtype, pk, pk_src):
+    """Times the c2-shaped conv kernels (32->32 3x3 over the 256x1836 mosaic: fwd, dgrad, wgrad)
+    alone on the current stream with CUDA events and reports the slowest against the bf16 peak."""
+    from driving_dirty_b200 import _lib
+    from driving_dirty_b200._lib import call, dtype_code, stream_ptr
+    dev = torch.device("cuda")
+    code = dtype_code(dtype)
+    H, W = VIEW_H, 6 * VIEW_W
+    x = torch.rand(batch, H, W, 32, device=dev).to(dtype)
+    dy = (torch.rand(batch, H, W, 32, device=dev) - 0.5).to(dtype)
+    out = torch.empty_like(x)
+    w = torch.rand(32, 32, 3, 3, device=dev) * 0.1
+    b = torch.zeros(32, device=dev)
+    dw, db = torch.empty_like(w), torch.empty_like(b)
+    n = int(_lib.load().dd_conv_wgrad_workspace_bytes())
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    st = stream_ptr()
+    kernels = {
+        "conv3x3_c32 fwd (c2)": lambda: call("dd_conv3x3_c32_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                             out.data_ptr(), code, batch, H, W, 1, 0, st),
+        "conv3x3_c32 dgrad (c2)": lambda: call("dd_conv3x3_c32_dgrad", dy.data_ptr(), w.data_ptr(), x.data_ptr(),
+                                               out.data_ptr(), code, batch, H, W, 1, 0, st),
+        "conv3x3_c32 wgrad (c2)": lambda: call("dd_conv3x3_c32_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                                               db.data_ptr(), ws.data_ptr(), n, code, batch, H, W, 1, 0, st),
+    }
+    flops = FLOP_C2_PER_SCENE * batch
+    rows = []
+    for name, fn in kernels.items():
+        t = time_kernel(fn)
+        rows.append({"kernel": name, "ms": t * 1e3, "tflops": flops / t / 1e12})
+    worst = max(rows, key=lambda r: r["ms"])
+    peak = pk["bf16_tflops"]
+    roof = {"bound": "tensor", "kernel": worst["kernel"], "achieved": worst["tflops"], "peak": peak,
+            "unit": "TFLOP/s", "frac": worst["tflops"] / peak, "traffic": None, "peak_source": pk_src + ", burst",
+            "algorithmic_flops_per_launch": flops, "ms_per_launch": worst["ms"], "all": rows}
+    del x, dy, out
+    torch.cuda.empty_cache()
+    return roof
+
+
+def hbm_kernel_rooflines(batch: int, pk):
+    """Stitch and fused BCE/TS kernels against the measured HBM copy bandwidth."""
+    from driving_dirty_b200 import ops
+    dev = torch.device("cuda")
+    views = torch.rand(batch, 6, 3, VIEW_H, VIEW_W, device=dev)
+    t = time_kernel(lambda: ops.stitch(views))
+    nbytes = 2 * views.numel() * 4
+    rows = [{"kernel": "stitch f32", "ms": t * 1e3, "gbs": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / pk["hbm_gbs"]}]
+    logits = torch.randn(batch, MAP, MAP, device=dev) * 0.06
+    target = (torch.rand(batch, MAP, MAP, device=dev) > 0.5).float()
+    t = time_kernel(lambda: ops.bce_threat(logits, target, want_probs=False, want_binary=False))
+    nbytes = 2 * logits.numel() * 4
+    rows.append({"kernel": "bce+ts fwd (f32 target, sums only)", "ms": t * 1e3, "gbs": nbytes / t / 1e9,
+                 "frac": nbytes / t / 1e9 / pk["hbm_gbs"]})
+    return rows
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from driving_dirty_b200 import _lib
+    from driving_dirty_b200.distributed import GradAllReducer
+    from oracle import scene_oracle as so
+
+    B = args.batch
+    model = build_model(args.dtype, dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    reducer = GradAllReducer(params)
+
+    # synthetic scenes: a different batch per rank, pinned on the host, one resident copy in HBM
+    views_h, road_h = so.synthetic_scene_batch(B, VIEW_H, VIEW_W, seed=20200506 + rank)
+    views_h, road_h = views_h.pin_memory(), road_h.pin_memory()
+    views_d, road_d = views_h.to(dev, non_blocking=True), road_h.to(dev, non_blocking=True)
+
+    def step(views, road):
+        opt.zero_grad(set_to_none=True)
+        out = model.training_step((views, None, road), 1)
+        out["loss"].backward()
+        reducer.finish()
+        opt.step()
+        return out["loss"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(views_d, road_d)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(views_d, road_d)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    sec = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if sampler else None
+    final_loss = float(loss)
+
+    # ---- end to end: host buffers in, loss out, every step -------------------------------------
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(views_d), torch.empty_like(road_d)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i][0].copy_(views_h, non_blocking=True)
+            bufs[i][1].copy_(road_h, non_blocking=True)
+            ready[i].record(copy_stream)
+
+    def e2e_loop(k):
+        prefetch(0)
+        for i in range(k):
+            cur = i & 1
+            torch.cuda.current_stream().wait_event(ready[cur])
+            if i + 1 < k:
+                copy_stream.wait_stream(torch.cuda.current_stream())   # buffer (i+1)&1 was consumed by step i-1
+                prefetch((i + 1) & 1)
+            l = step(bufs[cur][0], bufs[cur][1])
+            loss_h.copy_(l.detach(), non_blocking=False)               # D2H read of the step's result
+
+    e2e_loop(2)
+    barrier()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    sec_e2e = e0.elapsed_time(e1) * 1e-3
+
+    t = torch.tensor([sec, sec_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec, sec_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        adt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+        del bufs
+        torch.cuda.empty_cache()
+        roof = dominant_kernel_roofline(B, adt, pk, pk_src)
+        hbm_rows = hbm_kernel_rooflines(B, pk)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sps, csec = cpu_train_steps(args.cpu_batch, 3, 1)
+            cpu = {"value": sps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"3 steps of B={args.cpu_batch} scenes (fwd+BCE+TS+bwd+Adam) through oracle/scene_oracle.py "
+                             f"(torch CPU ops), {os.cpu_count()} threads, {csec:.2f} s/step"}
+        total = B * world * args.steps
+        line = {
+            "metric": METRIC, "value": total / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"RoadMapBCE train step (BASELINE config 2), {B} scenes/GPU/step, views 6x3x{VIEW_H}x{VIEW_W}, "
+                                   f"hidden {HIDDEN} latent {LATENT}, map {MAP}x{MAP}, encoder unfrozen, Adam(fused)",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "inputs (180 MB views/step) and activations (GBs) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": total / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": views_h.numel() * 4 + road_h.numel(),
+                    "d2h_bytes_per_step": 4, "ms_per_step": sec_e2e / args.steps * 1e3,
+                    "note": "pinned host views/road maps copied every step on a side stream (double-buffered), loss read back"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_rows,
+            "cpu_baseline": cpu, "final_loss": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

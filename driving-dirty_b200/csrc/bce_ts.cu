@@ -1,0 +1,300 @@
+// K9: one pass over the roadmap logits: sigmoid, BCE-with-logits sum, soft and rounded
+// threat-score sums, optional probs / binary map outputs; plus the BCE backward and MSE.
+// Reference: roadmap_bce_v2.py:81 (sigmoid), :103-106 (binary_cross_entropy_with_logits, mean),
+// :139-140 (compute_ts_road_map on probs and probs.round()), helper.py:74-77.
+// HBM-bound: algorithmic bytes per element = 4 (logit) + 4 or 1 (target) [+4 probs] [+1 binary].
+// Reduction is deterministic: per-CTA partials in the workspace, last CTA folds them in order.
+#include "dd_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = dd::kSMs * 8;
+constexpr int kSlots = 6;  // bce, sum_p, sum_tp, n_t, n_r, n_tr
+
+struct Workspace {
+  double partial[kMaxBlocks][kSlots];
+  unsigned int ticket;
+  unsigned int pad[3];
+};
+
+// round_half_even(sigmoid_fp32(x)) == 1  <=>  x > 1.5 * 2^-24  (bits 0x33C00000); established by
+// an exhaustive sweep of the reference's CPU sigmoid().round() (tests/golden/binarise.pt).
+__device__ __forceinline__ bool binarise(float x) { return x > __uint_as_float(0x33C00000u); }
+
+struct Acc {
+  float bce = 0.f, sp = 0.f, stp = 0.f;
+  int nt = 0, nr = 0, ntr = 0;
+};
+
+__device__ __forceinline__ void element(float x, float t, Acc& a, float& p, bool& r) {
+  const float e = expf(-fabsf(x));            // in (0, 1]
+  const float inv = __frcp_rn(1.0f + e);      // 1/(1+e), correctly rounded
+  p = x >= 0.f ? inv : e * inv;               // sigmoid(x)
+  // (1-t)*x + max(-x,0) + log1p(exp(-|x|))
+  a.bce += (1.0f - t) * x + fmaxf(-x, 0.f) + log1pf(e);
+  r = binarise(x);
+  a.sp += p;
+  a.stp += t * p;
+  const int ti = t != 0.f;
+  a.nt += ti;
+  a.nr += r;
+  a.ntr += ti & (int)r;
+}
+
+template <bool TU8>
+__global__ void __launch_bounds__(kThreads) bce_ts_kernel(const float* __restrict__ logits,
+                                                          const void* __restrict__ target_,
+                                                          float* __restrict__ probs,
+                                                          uint8_t* __restrict__ binary,
+                                                          float* __restrict__ stats,
+                                                          long long* __restrict__ counts,
+                                                          Workspace* __restrict__ ws, long long n) {
+  Acc a;
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldcs(reinterpret_cast<const float4*>(logits) + i);
+    float4 t;
+    if (TU8) {
+      const uchar4 u = __ldcs(reinterpret_cast<const uchar4*>(target_) + i);
+      t = make_float4(u.x != 0, u.y != 0, u.z != 0, u.w != 0);
+    } else {
+      t = __ldcs(reinterpret_cast<const float4*>(target_) + i);
+    }
+    float4 p;
+    bool r0, r1, r2, r3;
+    element(x.x, t.x, a, p.x, r0);
+    element(x.y, t.y, a, p.y, r1);
+    element(x.z, t.z, a, p.z, r2);
+    element(x.w, t.w, a, p.w, r3);
+    if (probs) __stcs(reinterpret_cast<float4*>(probs) + i, p);
+    if (binary) reinterpret_cast<uchar4*>(binary)[i] = make_uchar4(r0, r1, r2, r3);
+  }
+  // ragged tail (n % 4)
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += stride) {
+    const float x = logits[i];
+    const float t = TU8 ? (float)(reinterpret_cast<const uint8_t*>(target_)[i] != 0)
+                        : reinterpret_cast<const float*>(target_)[i];
+    float p;
+    bool r;
+    element(x, t, a, p, r);
+    if (probs) probs[i] = p;
+    if (binary) binary[i] = r;
+  }
+
+  // CTA reduction in double / int64
+  __shared__ double sred[kThreads / 32][kSlots];
+  double v[kSlots] = {(double)a.bce, (double)a.sp, (double)a.stp, (double)a.nt, (double)a.nr, (double)a.ntr};
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) v[s] = dd::warp_sum(v[s]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int s = 0; s < kSlots; ++s) sred[warp][s] = v[s];
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      double tot = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) tot += sred[w][s];
+      ws->partial[blockIdx.x][s] = tot;
+    }
+    __threadfence();
+    const unsigned int t = atomicAdd(&ws->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last CTA: fold partials in block order (deterministic)
+  if (threadIdx.x < kSlots) {
+    double tot = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(&ws->partial[b][threadIdx.x]);
+    sred[0][threadIdx.x] = tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double bce = sred[0][0], sp = sred[0][1], stp = sred[0][2];
+    const long long nt = (long long)sred[0][3], nr = (long long)sred[0][4], ntr = (long long)sred[0][5];
+    stats[0] = (float)(bce / (double)n);
+    // helper.py:74-77 in fp32: tp*1.0 / (a.sum() + b.sum() - tp)
+    const float tpf = (float)stp;
+    stats[1] = tpf / (((float)nt + (float)sp) - tpf);
+    const float tpr = (float)ntr;
+    stats[2] = tpr / (((float)nt + (float)nr) - tpr);
+    stats[3] = 0.f;
+    counts[0] = nt; counts[1] = nr; counts[2] = ntr; counts[3] = n;
+    ws->ticket = 0;  // self-reset for the next call on this stream
+  }
+}
+
+template <bool TU8>
+__global__ void __launch_bounds__(kThreads) bce_bwd_kernel(const float* __restrict__ logits,
+                                                           const void* __restrict__ target_,
+                                                           const float* __restrict__ grad_out,
+                                                           float* __restrict__ dlogits, long long n) {
+  const float scale = (grad_out ? __ldg(grad_out) : 1.0f) / (float)n;
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldcs(reinterpret_cast<const float4*>(logits) + i);
+    float4 t;
+    if (TU8) {
+      const uchar4 u = __ldcs(reinterpret_cast<const uchar4*>(target_) + i);
+      t = make_float4(u.x != 0, u.y != 0, u.z != 0, u.w != 0);
+    } else {
+      t = __ldcs(reinterpret_cast<const float4*>(target_) + i);
+    }
+    float4 g;
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    const float ts[4] = {t.x, t.y, t.z, t.w};
+    float gs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float e = expf(-fabsf(xs[k]));
+      const float inv = __frcp_rn(1.0f + e);
+      const float p = xs[k] >= 0.f ? inv : e * inv;
+      gs[k] = (p - ts[k]) * scale;
+    }
+    g = make_float4(gs[0], gs[1], gs[2], gs[3]);
+    reinterpret_cast<float4*>(dlogits)[i] = g;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += stride) {
+    const float x = logits[i];
+    const float t = TU8 ? (float)(reinterpret_cast<const uint8_t*>(target_)[i] != 0)
+                        : reinterpret_cast<const float*>(target_)[i];
+    const float e = expf(-fabsf(x));
+    const float inv = __frcp_rn(1.0f + e);
+    dlogits[i] = ((x >= 0.f ? inv : e * inv) - t) * scale;
+  }
+}
+
+// generic two-map sums: MODE 0 = threat score (sum a*b, sum a, sum b); MODE 1 = squared error
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) pair_reduce_kernel(const float* __restrict__ a,
+                                                               const float* __restrict__ b,
+                                                               float* __restrict__ out,
+                                                               Workspace* __restrict__ ws, long long n) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += stride) {
+    const float x = a[i], y = b[i];
+    if (MODE == 0) { s0 += x * y; s1 += x; s2 += y; }
+    else { const float d = x - y; s0 += d * d; }
+  }
+  __shared__ double sred[kThreads / 32][3];
+  double v[3] = {(double)s0, (double)s1, (double)s2};
+  for (int s = 0; s < 3; ++s) v[s] = dd::warp_sum(v[s]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) for (int s = 0; s < 3; ++s) sred[warp][s] = v[s];
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 3; ++s) {
+      double tot = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) tot += sred[w][s];
+      ws->partial[blockIdx.x][s] = tot;
+    }
+    __threadfence();
+    is_last = (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 3) {
+    double tot = 0.0;
+    for (unsigned int k = 0; k < gridDim.x; ++k) tot += __ldcg(&ws->partial[k][threadIdx.x]);
+    sred[0][threadIdx.x] = tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (MODE == 0) {
+      const float tp = (float)sred[0][0];
+      out[0] = tp / (((float)sred[0][1] + (float)sred[0][2]) - tp);
+    } else {
+      out[0] = (float)(sred[0][0] / (double)n);
+    }
+    ws->ticket = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) mse_bwd_kernel(const float* __restrict__ y,
+                                                           const float* __restrict__ y_hat,
+                                                           const float* __restrict__ grad_out,
+                                                           float* __restrict__ dy_hat, long long n) {
+  // F.mse_loss(y, y_hat): d/dy_hat mean((y - y_hat)^2) = 2 (y_hat - y) / n
+  const float scale = 2.0f * (grad_out ? __ldg(grad_out) : 1.0f) / (float)n;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += stride)
+    dy_hat[i] = (y_hat[i] - y[i]) * scale;
+}
+
+int grid_for(long long n) {
+  long long g = (n / 4 + kThreads - 1) / kThreads;
+  if (g < 1) g = 1;
+  return (int)(g < kMaxBlocks ? g : kMaxBlocks);
+}
+}  // namespace
+
+extern "C" size_t dd_bce_ts_workspace_bytes(void) { return sizeof(Workspace); }
+
+extern "C" int dd_bce_ts_fwd(const float* logits, const void* target, int target_is_u8, float* probs,
+                             uint8_t* binary, float* stats, long long* counts, void* workspace,
+                             size_t ws_bytes, long long n, void* stream) {
+  DD_REQUIRE(logits && target && stats && counts && workspace, DD_ERR_BAD_ARG, "dd_bce_ts_fwd: null pointer");
+  DD_REQUIRE(n > 0, DD_ERR_BAD_ARG, "dd_bce_ts_fwd: n=%lld", n);
+  DD_REQUIRE(ws_bytes >= sizeof(Workspace), DD_ERR_WORKSPACE, "dd_bce_ts_fwd: workspace %zu < %zu", ws_bytes,
+             sizeof(Workspace));
+  DD_REQUIRE((uintptr_t)logits % 16 == 0 && (uintptr_t)target % (target_is_u8 ? 4 : 16) == 0 &&
+                 (!probs || (uintptr_t)probs % 16 == 0) && (!binary || (uintptr_t)binary % 4 == 0),
+             DD_ERR_ALIGNMENT, "dd_bce_ts_fwd: pointers must be 16-byte aligned");
+  const int grid = grid_for(n);
+  if (target_is_u8)
+    bce_ts_kernel<true><<<grid, kThreads, 0, dd::as_stream(stream)>>>(logits, target, probs, binary, stats, counts,
+                                                                      (Workspace*)workspace, n);
+  else
+    bce_ts_kernel<false><<<grid, kThreads, 0, dd::as_stream(stream)>>>(logits, target, probs, binary, stats, counts,
+                                                                       (Workspace*)workspace, n);
+  return dd::check_launch("bce_ts_fwd");
+}
+
+extern "C" int dd_bce_bwd(const float* logits, const void* target, int target_is_u8, const float* grad_out,
+                          float* dlogits, long long n, void* stream) {
+  DD_REQUIRE(logits && target && dlogits, DD_ERR_BAD_ARG, "dd_bce_bwd: null pointer");
+  DD_REQUIRE(n > 0, DD_ERR_BAD_ARG, "dd_bce_bwd: n=%lld", n);
+  DD_REQUIRE((uintptr_t)logits % 16 == 0 && (uintptr_t)target % (target_is_u8 ? 4 : 16) == 0 &&
+                 (uintptr_t)dlogits % 16 == 0,
+             DD_ERR_ALIGNMENT, "dd_bce_bwd: pointers must be 16-byte aligned");
+  const int grid = grid_for(n);
+  if (target_is_u8)
+    bce_bwd_kernel<true><<<grid, kThreads, 0, dd::as_stream(stream)>>>(logits, target, grad_out, dlogits, n);
+  else
+    bce_bwd_kernel<false><<<grid, kThreads, 0, dd::as_stream(stream)>>>(logits, target, grad_out, dlogits, n);
+  return dd::check_launch("bce_bwd");
+}
+
+extern "C" int dd_threat_score_f32(const float* a, const float* b, float* ts, void* workspace, size_t ws_bytes,
+                                   long long n, void* stream) {
+  DD_REQUIRE(a && b && ts && workspace, DD_ERR_BAD_ARG, "dd_threat_score_f32: null pointer");
+  DD_REQUIRE(n > 0, DD_ERR_BAD_ARG, "dd_threat_score_f32: n=%lld", n);
+  DD_REQUIRE(ws_bytes >= sizeof(Workspace), DD_ERR_WORKSPACE, "dd_threat_score_f32: workspace too small");
+  pair_reduce_kernel<0><<<grid_for(n * 4), kThreads, 0, dd::as_stream(stream)>>>(a, b, ts, (Workspace*)workspace, n);
+  return dd::check_launch("threat_score");
+}
+
+extern "C" int dd_mse_fwd(const float* y, const float* y_hat, float* loss, void* workspace, size_t ws_bytes,
+                          long long n, void* stream) {
+  DD_REQUIRE(y && y_hat && loss && workspace, DD_ERR_BAD_ARG, "dd_mse_fwd: null pointer");
+  DD_REQUIRE(n > 0, DD_ERR_BAD_ARG, "dd_mse_fwd: n=%lld", n);
+  DD_REQUIRE(ws_bytes >= sizeof(Workspace), DD_ERR_WORKSPACE, "dd_mse_fwd: workspace too small");
+  pair_reduce_kernel<1><<<grid_for(n * 4), kThreads, 0, dd::as_stream(stream)>>>(y, y_hat, loss, (Workspace*)workspace, n);
+  return dd::check_launch("mse_fwd");
+}
+
+extern "C" int dd_mse_bwd(const float* y, const float* y_hat, const float* grad_out, float* dy_hat, long long n,
+                          void* stream) {
+  DD_REQUIRE(y && y_hat && dy_hat, DD_ERR_BAD_ARG, "dd_mse_bwd: null pointer");
+  DD_REQUIRE(n > 0, DD_ERR_BAD_ARG, "dd_mse_bwd: n=%lld", n);
+  mse_bwd_kernel<<<grid_for(n * 4), kThreads, 0, dd::as_stream(stream)>>>(y, y_hat, grad_out, dy_hat, n);
+  return dd::check_launch("mse_bwd");
+}

@@ -1,0 +1,374 @@
+"""Host-side operators over the C ABI (include/dd_b200.h): thin wrappers and the
+``torch.autograd.Function``s the drop-in modules are built from.
+
+PyTorch is plumbing here -- it owns device memory, streams and the autograd tape; every byte
+of arithmetic on the scene path is done by libdd_b200.so.  There is no CPU path: tensors that
+are not CUDA tensors raise.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import _lib
+from ._lib import DD_BF16, DD_F32, IMPL_AUTO, call, dtype_code, stream_ptr
+
+VIEW_ORDER = (0, 1, 2, 5, 4, 3)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("driving-dirty_b200 runs on CUDA (sm_100a) only; got a CPU tensor. "
+                               "There is no CPU fallback on this path.")
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _Workspaces:
+    """Per-device scratch buffers (owned by torch's allocator, handed to the library per call)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key: str, nbytes: int, device, zero: bool = False) -> torch.Tensor:
+        k = (key, device.index)
+        buf = self._bufs.get(k)
+        if buf is None or buf.numel() < nbytes:
+            buf = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self._bufs[k] = buf
+        return buf
+
+
+_ws = _Workspaces()
+
+
+# --------------------------------------------------------------------------------------------
+# input handling / stitch
+# --------------------------------------------------------------------------------------------
+def as_view_batch(sample) -> torch.Tensor:
+    """tuple/list of B [6,3,H,W] tensors (what collate_fn yields) or a [B,6,3,H,W] tensor ->
+    contiguous [B,6,3,H,W] fp32 CUDA tensor, without a copy when the tuple is ``batch.unbind(0)``."""
+    if torch.is_tensor(sample):
+        x = sample
+    else:
+        sample = tuple(sample)
+        first = sample[0]
+        base = first._base
+        zero_copy = (base is not None and base.dim() == 5 and base.is_contiguous() and base.shape[0] == len(sample)
+                     and all(s._base is base and s.storage_offset() == base.storage_offset() + i * first.numel()
+                             and s.is_contiguous() for i, s in enumerate(sample)))
+        x = base if zero_copy else torch.stack(sample, dim=0)
+    _require_cuda(x)
+    if x.dim() != 5 or x.shape[1] != 6 or x.shape[2] != 3:
+        raise RuntimeError(f"expected views of shape [B,6,3,H,W], got {tuple(x.shape)}")
+    if x.dtype != torch.float32:
+        x = x.float()
+    return _c(x)
+
+
+def stitch(views: torch.Tensor) -> torch.Tensor:
+    """wide_stitch_six_images (roadmap_bce_v2.py:53-64): [B,6,3,H,W] -> [B,3,H,6W]."""
+    views = as_view_batch(views)
+    B, _, _, H, W = views.shape
+    out = torch.empty(B, 3, H, 6 * W, dtype=torch.float32, device=views.device)
+    call("dd_stitch_f32", views.data_ptr(), out.data_ptr(), B, H, W, stream_ptr())
+    return out
+
+
+def stitch_u8(views_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 camera bytes [B,6,3,H,W] -> fp32 mosaic with the ToTensor /255 folded in."""
+    _require_cuda(views_u8)
+    views_u8 = _c(views_u8)
+    B, _, _, H, W = views_u8.shape
+    out = torch.empty(B, 3, H, 6 * W, dtype=torch.float32, device=views_u8.device)
+    call("dd_stitch_u8", views_u8.data_ptr(), out.data_ptr(), B, H, W, stream_ptr())
+    return out
+
+
+def stitch_mask(views: torch.Tensor, slot: int):
+    """six_to_one_task (autoencoder.py:53-73) for an already drawn slot: (x, y)."""
+    views = as_view_batch(views)
+    B, _, _, H, W = views.shape
+    x = torch.empty(B, 3, H, 6 * W, dtype=torch.float32, device=views.device)
+    y = torch.empty(B, 3, H, W, dtype=torch.float32, device=views.device)
+    call("dd_stitch_mask_f32", views.data_ptr(), x.data_ptr(), y.data_ptr(), B, H, W, int(slot), stream_ptr())
+    return x, y
+
+
+# --------------------------------------------------------------------------------------------
+# encoder conv stack (c1 -> c2 -> c3 [-> flat max-pool]) as ONE autograd node
+# --------------------------------------------------------------------------------------------
+def _conv_ws(device):
+    n = int(_lib.load().dd_conv_wgrad_workspace_bytes())
+    return _ws.get("conv_wgrad", n, device), n
+
+
+class EncoderConvStack(torch.autograd.Function):
+    """relu(c1) -> relu(c2) -> relu(c3, stride 2) -> view(B,-1) -> max_pool1d(4)
+    (components.py:41-47).  ``inp`` is the views batch [B,6,3,H,W] (stitch folded into c1's loads)
+    or a mosaic / NCHW image [B,3,H,Wm].  Activations are NHWC in ``act_dtype``.  Returns the
+    pooled features [B, 8*H3*W3] (act_dtype) or, with ``c3_only``, the c3 activation as NCHW fp32
+    (components.py:44-45)."""
+
+    @staticmethod
+    def forward(ctx, inp, w1, b1, w2, b2, w3, b3, act_dtype, c3_only, impl):
+        _require_cuda(inp, w1, w2, w3)
+        inp = _c(inp)
+        is_views = inp.dim() == 5
+        if is_views:
+            B, _, _, H, W = inp.shape
+            Wm = 6 * W
+        else:
+            B, _, H, Wm = inp.shape
+        dev, code, st = inp.device, dtype_code(act_dtype), stream_ptr()
+        H3, W3 = (H - 1) // 2 + 1, (Wm - 1) // 2 + 1
+        w1, b1, w2, b2, w3, b3 = (_c(t.detach().float()) for t in (w1, b1, w2, b2, w3, b3))
+        a1 = torch.empty(B, H, Wm, 32, dtype=act_dtype, device=dev)
+        call("dd_conv_c1_fwd", inp.data_ptr(), int(is_views), w1.data_ptr(), b1.data_ptr(), a1.data_ptr(), code,
+             B, H, Wm, st)
+        a2 = torch.empty_like(a1)
+        call("dd_conv3x3_c32_fwd", a1.data_ptr(), w2.data_ptr(), b2.data_ptr(), a2.data_ptr(), code, B, H, Wm, 1,
+             impl, st)
+        a3 = torch.empty(B, H3, W3, 32, dtype=act_dtype, device=dev)
+        call("dd_conv3x3_c32_fwd", a2.data_ptr(), w3.data_ptr(), b3.data_ptr(), a3.data_ptr(), code, B, H, Wm, 2,
+             impl, st)
+        if c3_only:
+            out = torch.empty(B, 32, H3, W3, dtype=torch.float32, device=dev)
+            call("dd_nhwc_to_nchw_f32", a3.data_ptr(), code, out.data_ptr(), B, 32, H3, W3, st)
+        else:
+            out = torch.empty(B, 8 * H3 * W3, dtype=act_dtype, device=dev)
+            call("dd_pool4_fwd", a3.data_ptr(), out.data_ptr(), code, B, H3, W3, st)
+        ctx.geom = (B, H, Wm, H3, W3, is_views, code, c3_only, impl, act_dtype)
+        ctx.save_for_backward(inp, w2, w3, a1, a2, a3)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        inp, w2, w3, a1, a2, a3 = ctx.saved_tensors
+        B, H, Wm, H3, W3, is_views, code, c3_only, impl, act_dtype = ctx.geom
+        dev, st = g.device, stream_ptr()
+        ws, ws_n = _conv_ws(dev)
+        da3 = torch.empty_like(a3)
+        if c3_only:
+            g = _c(g.float())
+            call("dd_nchw_f32_to_nhwc", g.data_ptr(), da3.data_ptr(), code, B, 32, H3, W3, st)
+            call("dd_relu_mask", da3.data_ptr(), a3.data_ptr(), da3.data_ptr(), code, da3.numel(), st)
+        else:
+            g = _c(g.to(act_dtype))
+            call("dd_pool4_bwd", a3.data_ptr(), g.data_ptr(), da3.data_ptr(), code, B, H3, W3, st)
+        f32 = dict(dtype=torch.float32, device=dev)
+        dw3, db3 = torch.empty(32, 32, 3, 3, **f32), torch.empty(32, **f32)
+        call("dd_conv3x3_c32_wgrad", a2.data_ptr(), da3.data_ptr(), dw3.data_ptr(), db3.data_ptr(), ws.data_ptr(),
+             ws_n, code, B, H, Wm, 2, impl, st)
+        da2 = torch.empty_like(a2)
+        call("dd_conv3x3_c32_dgrad", da3.data_ptr(), w3.data_ptr(), a2.data_ptr(), da2.data_ptr(), code, B, H, Wm, 2,
+             impl, st)
+        del da3
+        dw2, db2 = torch.empty(32, 32, 3, 3, **f32), torch.empty(32, **f32)
+        call("dd_conv3x3_c32_wgrad", a1.data_ptr(), da2.data_ptr(), dw2.data_ptr(), db2.data_ptr(), ws.data_ptr(),
+             ws_n, code, B, H, Wm, 1, impl, st)
+        da1 = torch.empty_like(a1)
+        call("dd_conv3x3_c32_dgrad", da2.data_ptr(), w2.data_ptr(), a1.data_ptr(), da1.data_ptr(), code, B, H, Wm, 1,
+             impl, st)
+        del da2
+        dw1, db1 = torch.empty(32, 3, 3, 3, **f32), torch.empty(32, **f32)
+        call("dd_conv_c1_wgrad", inp.data_ptr(), int(is_views), da1.data_ptr(), code, dw1.data_ptr(), db1.data_ptr(),
+             ws.data_ptr(), ws_n, B, H, Wm, st)
+        return None, dw1, db1, dw2, db2, dw3, db3, None, None, None
+
+
+def encoder_conv_stack(inp, c1, c2, c3, act_dtype=torch.float32, c3_only=False, impl=IMPL_AUTO):
+    return EncoderConvStack.apply(inp, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, act_dtype,
+                                  bool(c3_only), int(impl))
+
+
+# --------------------------------------------------------------------------------------------
+# skinny linear
+# --------------------------------------------------------------------------------------------
+def _linear_ws(B, N, K, device):
+    n = int(_lib.load().dd_linear_workspace_bytes(B, N, K))
+    return _ws.get("linear", n, device), n
+
+
+class SkinnyLinear(torch.autograd.Function):
+    """y = x W^T + b for a small batch and a very wide K or N (nn.Linear at components.py:105,
+    roadmap_bce_v2.py:75).  x: [B,K] fp32 or bf16; W [N,K], b [N], y [B,N] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, impl):
+        _require_cuda(x, w)
+        x, wd = _c(x), _c(w.detach())
+        if wd.dtype != torch.float32:
+            wd = wd.float()
+        B, K = x.shape
+        N = wd.shape[0]
+        y = torch.empty(B, N, dtype=torch.float32, device=x.device)
+        ws, n = _linear_ws(B, N, K, x.device)
+        bias_ptr = _c(b.detach().float()).data_ptr() if b is not None else None
+        call("dd_linear_fwd", x.data_ptr(), dtype_code(x.dtype), wd.data_ptr(), bias_ptr, y.data_ptr(),
+             ws.data_ptr(), n, B, N, K, impl, stream_ptr())
+        ctx.save_for_backward(x, wd)
+        ctx.has_bias = b is not None
+        ctx.impl = impl
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        B, K = x.shape
+        N = w.shape[0]
+        dy = _c(dy.float())
+        st = stream_ptr()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ws, n = _linear_ws(B, N, K, x.device)
+            call("dd_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), dtype_code(x.dtype), ws.data_ptr(), n,
+                 B, N, K, ctx.impl, st)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            db = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            call("dd_linear_wgrad", dy.data_ptr(), x.data_ptr(), dtype_code(x.dtype), dw.data_ptr(),
+                 db.data_ptr() if db is not None else None, B, N, K, ctx.impl, st)
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, impl=IMPL_AUTO):
+    return SkinnyLinear.apply(x, weight, bias, int(impl))
+
+
+# --------------------------------------------------------------------------------------------
+# sigmoid + BCE + threat score + binarise
+# --------------------------------------------------------------------------------------------
+def _bce_ws(device):
+    n = int(_lib.load().dd_bce_ts_workspace_bytes())
+    return _ws.get("bce_ts", n, device, zero=True), n
+
+
+class BceThreat(torch.autograd.Function):
+    """One pass: mean BCE-with-logits (roadmap_bce_v2.py:103-106), probs = sigmoid (:81),
+    binary = probs.round() (:140), TS(target, probs) and TS(target, binary) (helper.py:74-77).
+    Returns (loss, probs, binary_u8, stats[4], counts[4]); only ``loss`` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, logits, target, want_probs, want_binary):
+        _require_cuda(logits, target)
+        logits = _c(logits)
+        if logits.dtype != torch.float32:
+            raise RuntimeError("roadmap logits must be fp32")
+        target = _c(target)
+        is_u8 = target.dtype in (torch.uint8, torch.bool)
+        if not is_u8 and target.dtype != torch.float32:
+            target = target.float()
+        n = logits.numel()
+        if target.numel() != n:
+            raise RuntimeError(f"target has {target.numel()} elements, logits {n}")
+        dev = logits.device
+        probs = torch.empty_like(logits) if want_probs else None
+        binary = torch.empty(logits.shape, dtype=torch.uint8, device=dev) if want_binary else None
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        counts = torch.empty(4, dtype=torch.int64, device=dev)
+        ws, wn = _bce_ws(dev)
+        call("dd_bce_ts_fwd", logits.data_ptr(), target.data_ptr(), int(is_u8),
+             probs.data_ptr() if want_probs else None, binary.data_ptr() if want_binary else None,
+             stats.data_ptr(), counts.data_ptr(), ws.data_ptr(), wn, n, stream_ptr())
+        ctx.save_for_backward(logits, target)
+        ctx.is_u8 = is_u8
+        loss = stats[0].clone()
+        outs = (loss, probs, binary, stats, counts)
+        ctx.mark_non_differentiable(*[t for t in outs[1:] if t is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        logits, target = ctx.saved_tensors
+        dlogits = torch.empty_like(logits)
+        g = _c(g_loss.float().reshape(1))
+        call("dd_bce_bwd", logits.data_ptr(), target.data_ptr(), int(ctx.is_u8), g.data_ptr(), dlogits.data_ptr(),
+             logits.numel(), stream_ptr())
+        return dlogits, None, None, None
+
+
+def bce_threat(logits, target, want_probs=True, want_binary=True):
+    return BceThreat.apply(logits, target, bool(want_probs), bool(want_binary))
+
+
+class _SigmoidBinary(torch.autograd.Function):
+    """forward()'s ``torch.sigmoid(y)`` (roadmap_bce_v2.py:81) plus the binarised map, through the
+    same kernel with a dummy all-zero target (statistics discarded)."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        logits = _c(logits)
+        dev = logits.device
+        probs = torch.empty_like(logits)
+        binary = torch.empty(logits.shape, dtype=torch.uint8, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        counts = torch.empty(4, dtype=torch.int64, device=dev)
+        ws, wn = _bce_ws(dev)
+        # the binary map doubles as the (ignored) u8 target: it is written after being read per element
+        zeros = torch.zeros(logits.shape, dtype=torch.uint8, device=dev)
+        call("dd_bce_ts_fwd", logits.data_ptr(), zeros.data_ptr(), 1, probs.data_ptr(), binary.data_ptr(),
+             stats.data_ptr(), counts.data_ptr(), ws.data_ptr(), wn, logits.numel(), stream_ptr())
+        ctx.save_for_backward(probs)
+        ctx.mark_non_differentiable(binary)
+        return probs, binary
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (p,) = ctx.saved_tensors
+        return g * p * (1.0 - p)
+
+
+def sigmoid_binary(logits):
+    return _SigmoidBinary.apply(logits)
+
+
+def threat_score(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """compute_ts_road_map (helper.py:74-77) for two maps of any float values -> 0-dim tensor."""
+    _require_cuda(a, b)
+    a, b = _c(a.float()), _c(b.float())
+    if a.numel() != b.numel():
+        raise RuntimeError("threat_score: maps differ in size")
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    ws, wn = _bce_ws(a.device)
+    call("dd_threat_score_f32", a.data_ptr(), b.data_ptr(), out.data_ptr(), ws.data_ptr(), wn, a.numel(), stream_ptr())
+    return out[0]
+
+
+class MseLoss(torch.autograd.Function):
+    """F.mse_loss(y, y_hat) (autoencoder.py:91), mean over all elements."""
+
+    @staticmethod
+    def forward(ctx, y, y_hat):
+        _require_cuda(y, y_hat)
+        y, y_hat = _c(y.float()), _c(y_hat.float())
+        out = torch.empty(1, dtype=torch.float32, device=y.device)
+        ws, wn = _bce_ws(y.device)
+        call("dd_mse_fwd", y.data_ptr(), y_hat.data_ptr(), out.data_ptr(), ws.data_ptr(), wn, y.numel(), stream_ptr())
+        ctx.save_for_backward(y, y_hat)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        y, y_hat = ctx.saved_tensors
+        d = torch.empty_like(y_hat)
+        gg = _c(g.float().reshape(1))
+        call("dd_mse_bwd", y.data_ptr(), y_hat.data_ptr(), gg.data_ptr(), d.data_ptr(), y.numel(), stream_ptr())
+        return (-d if ctx.needs_input_grad[0] else None), d
+
+
+def mse_loss(y, y_hat):
+    return MseLoss.apply(y, y_hat)
+
+
+def decoder_deconv_stack(x, dc1, dc2, dc3, dc4):
+    """Decoder transposed-conv stack (components.py:88-92).  Kernels not built yet in this round;
+    fails loudly rather than falling back to a library path."""
+    raise RuntimeError("decoder transposed-conv kernels are not built yet (BasicAE decode path, SURVEY A13)")

@@ -1,0 +1,143 @@
+/*
+ * dd_b200.h -- C ABI of the B200-native six-camera scene pipeline (libdd_b200.so).
+ *
+ * The reference (annikabrundyn/driving-dirty) has no FFI: its hot path is PyTorch calls made
+ * from LightningModule methods.  Each entry point below replaces the torch call(s) at the cited
+ * reference lines (paths relative to /root/reference/src); INTEGRATION.md shows the ctypes stub
+ * a maintainer adds at each site.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator); the library
+ *    never allocates, frees or retains device memory.  `stream` is a cudaStream_t passed as
+ *    void*; work is only enqueued on it, nothing synchronises the host.
+ *  - Return value: 0 = ok, <0 = dd_status (bad argument / unsupported shape / wrong arch),
+ *    >0 = cudaError_t from the launch.  dd_last_error() gives the text.  No fallbacks.
+ *  - Activations inside the conv stack are NHWC ("pixel-major": [B][H][W][32 channels]), in
+ *    fp32 (DD_F32) or bf16 (DD_BF16).  Weights, biases, gradients of weights, logits, losses
+ *    are fp32 in torch layouts (OIHW, [out,in]).
+ *  - "mosaic" = the 3 x H x 6W stitched image; "views" = the six 3 x H x W camera images of a
+ *    scene in dataset order; slot j of the mosaic holds view DD_VIEW_ORDER[j] = {0,1,2,5,4,3}.
+ */
+#ifndef DD_B200_H
+#define DD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { DD_F32 = 0, DD_BF16 = 1 } dd_dtype;
+
+typedef enum {
+  DD_OK = 0,
+  DD_ERR_BAD_ARG = -1,      /* null pointer, non-positive size */
+  DD_ERR_UNSUPPORTED = -2,  /* shape/stride/dtype combination not implemented */
+  DD_ERR_WORKSPACE = -3,    /* workspace too small (see dd_*_workspace_bytes) */
+  DD_ERR_ALIGNMENT = -4,    /* pointer not aligned as the kernel requires */
+  DD_ERR_ARCH = -5          /* device is not sm_100 */
+} dd_status;
+
+/* How a conv entry point should run: AUTO picks tcgen05 for bf16 where implemented. */
+typedef enum { DD_IMPL_AUTO = 0, DD_IMPL_SIMT = 1, DD_IMPL_TCGEN05 = 2 } dd_impl;
+
+int dd_version(void);
+/* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
+int dd_last_error(char* buf, size_t len);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+long long dd_launch_count(void);
+
+/* ---- A1/A2: stitch ------------------------------------------------------------------------
+ * roadmap_bce_v2.py:53-64 wide_stitch_six_images; autoencoder.py:53-73 six_to_one_task.
+ * views [B,6,3,H,W] f32 -> mosaic [B,3,H,6W] f32.  The mask variant also writes
+ * y [B,3,H,W] = mosaic[..., slot*W:(slot+1)*W] and zeroes that block of x. */
+int dd_stitch_f32(const float* views, float* mosaic, int B, int H, int W, void* stream);
+int dd_stitch_mask_f32(const float* views, float* x, float* y, int B, int H, int W, int slot,
+                       void* stream);
+/* Front-end for raw camera bytes (data_helper.py:109-114 ToTensor): views u8 [B,6,3,H,W] ->
+ * mosaic f32 with value/255 (bit-identical to x.float()/255). */
+int dd_stitch_u8(const uint8_t* views, float* mosaic, int B, int H, int W, void* stream);
+
+/* ---- A3: encoder convs (components.py:19-21,41-43) ------------------------------------------
+ * c1: 3->32, 3x3, pad 1, + bias + ReLU.  `in` is either the views [B,6,3,H,W] (in_is_views=1:
+ * the stitch is folded into the loads, Wm = 6W) or a mosaic / any NCHW image [B,3,H,Wm]
+ * (in_is_views=0).  out: NHWC [B,H,Wm,32] of out_dtype. */
+int dd_conv_c1_fwd(const float* in, int in_is_views, const float* w_oihw, const float* bias,
+                   void* out, int out_dtype, int B, int H, int Wm, void* stream);
+/* dW [32,3,3,3], db [32] from dy = dL/d(out) ALREADY masked by out>0.  workspace: see below. */
+int dd_conv_c1_wgrad(const float* in, int in_is_views, const void* dy, int dtype, float* dw,
+                     float* db, void* workspace, size_t ws_bytes, int B, int H, int Wm,
+                     void* stream);
+
+/* c2 / c3: 32->32, 3x3, pad 1, stride 1 or 2, + bias + ReLU; NHWC in [B,H,W,32] ->
+ * NHWC out [B,Ho,Wo,32], Ho = (H-1)/stride+1. */
+int dd_conv3x3_c32_fwd(const void* in, const float* w_oihw, const float* bias, void* out,
+                       int dtype, int B, int H, int W, int stride, int impl, void* stream);
+/* dx [B,H,W,32] = conv_transpose(dy, w) * (x > 0)   (x = this layer's input = previous
+ * layer's post-ReLU output; pass x = NULL for no mask).  dy must already be masked. */
+int dd_conv3x3_c32_dgrad(const void* dy, const float* w_oihw, const void* x, void* dx,
+                         int dtype, int B, int H, int W, int stride, int impl, void* stream);
+/* dW [32,32,3,3] f32, db [32] f32 (overwritten, deterministic reduction order). */
+int dd_conv3x3_c32_wgrad(const void* x, const void* dy, float* dw, float* db, void* workspace,
+                         size_t ws_bytes, int dtype, int B, int H, int W, int stride, int impl,
+                         void* stream);
+size_t dd_conv_wgrad_workspace_bytes(void);
+
+/* ---- A5: flatten + max_pool1d(4) over the NCHW-flat index (components.py:46-47) -------------
+ * a3 NHWC [B,H,W,32] -> pooled [B, (32*H*W)/4] in the reference's feature order.
+ * bwd: da3 = scatter of dpooled to the FIRST max of each window, times (a3 > 0). */
+int dd_pool4_fwd(const void* a3, void* pooled, int dtype, int B, int H, int W, void* stream);
+int dd_pool4_bwd(const void* a3, const void* dpooled, void* da3, int dtype, int B, int H, int W,
+                 void* stream);
+
+/* Layout changes at the API edge (c3_only "ssr" output, components.py:44-45; tests). */
+int dd_nhwc_to_nchw_f32(const void* in, int in_dtype, float* out, int B, int C, int H, int W,
+                        void* stream);
+int dd_nchw_f32_to_nhwc(const float* in, void* out, int out_dtype, int B, int C, int H, int W,
+                        void* stream);
+/* g_masked = g * (act > 0), NHWC tensors of `dtype`, n elements. */
+int dd_relu_mask(const void* g, const void* act, void* out, int dtype, long long n, void* stream);
+
+/* ---- A6/A8: skinny linear layers (components.py:100,105; roadmap_bce_v2.py:50,75) -----------
+ * y[B,N] = x[B,K] W[N,K]^T + bias.  W, bias, y, dW, db fp32; x / dx of x_dtype.  B <= 64.
+ * Used for Encoder.fc1.fc1 (K = 940032), the roadmap head (N = 640000), Decoder.fc2.fc1. */
+int dd_linear_fwd(const void* x, int x_dtype, const float* w, const float* bias, float* y,
+                  void* workspace, size_t ws_bytes, int B, int N, long long K, int impl,
+                  void* stream);
+int dd_linear_dgrad(const float* dy, const float* w, void* dx, int dx_dtype, void* workspace,
+                    size_t ws_bytes, int B, int N, long long K, int impl, void* stream);
+int dd_linear_wgrad(const float* dy, const void* x, int x_dtype, float* dw, float* db, int B,
+                    int N, long long K, int impl, void* stream);
+size_t dd_linear_workspace_bytes(int B, int N, long long K);
+
+/* ---- A8-A11: sigmoid + BCE-with-logits + threat scores + binarise -----------------------------
+ * roadmap_bce_v2.py:81 (sigmoid), :106 (binary_cross_entropy_with_logits, mean), :140 (.round()),
+ * helper.py:74-77 (compute_ts_road_map, soft and rounded), in ONE pass over logits/target.
+ * target: f32 {0,1} (target_is_u8=0) or u8/bool (1).  Optional outputs may be NULL:
+ *   probs  f32 [n]  = sigmoid(logits)
+ *   binary u8  [n]  = round_half_even(sigmoid(logits))  (== logits > 1.5*2^-24)
+ * stats f32[4]  = {mean BCE, TS(target, probs), TS(target, binary), 0}
+ * counts i64[4] = {sum target, sum binary, sum target*binary, n}
+ * workspace: dd_bce_ts_workspace_bytes() bytes, zeroed by the caller ONCE (self-resetting). */
+int dd_bce_ts_fwd(const float* logits, const void* target, int target_is_u8, float* probs,
+                  uint8_t* binary, float* stats, long long* counts, void* workspace,
+                  size_t ws_bytes, long long n, void* stream);
+/* dlogits = (sigmoid(logits) - target) * (*grad_out) / n   (grad_out: device scalar or NULL=1) */
+int dd_bce_bwd(const float* logits, const void* target, int target_is_u8, const float* grad_out,
+               float* dlogits, long long n, void* stream);
+size_t dd_bce_ts_workspace_bytes(void);
+/* Standalone helper.py:74-77 on two f32 maps (any values): ts f32[1]. */
+int dd_threat_score_f32(const float* a, const float* b, float* ts, void* workspace,
+                        size_t ws_bytes, long long n, void* stream);
+
+/* ---- A14: mean squared error (autoencoder.py:91) ---------------------------------------------*/
+int dd_mse_fwd(const float* y, const float* y_hat, float* loss, void* workspace, size_t ws_bytes,
+               long long n, void* stream);
+int dd_mse_bwd(const float* y, const float* y_hat, const float* grad_out, float* dy_hat,
+               long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DD_B200_H */

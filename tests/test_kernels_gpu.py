@@ -1,0 +1,301 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle on the same seeded inputs.
+Bit-exact for index / byte / count work; fp32 within 1e-5 and bf16 within 1e-2 of max|ref|."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import scene_oracle as so
+from tests.helpers import rel_max_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def dd():
+    from driving_dirty_b200 import _lib, ops
+    assert torch.cuda.is_available()
+    _lib.load()
+    return ops
+
+
+def nhwc(x_nchw, dtype):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+
+
+def to_nchw(x_nhwc):
+    return x_nhwc.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def q(x, dtype):
+    """round-trip through the storage dtype so the oracle sees what the kernel reads"""
+    return x.to(dtype).float()
+
+
+# ------------------------------------------------------------------------------- stitch ------
+@pytest.mark.parametrize("B,H,W", [(1, 4, 6), (3, 16, 20), (2, 5, 7), (2, 256, 306)])
+def test_stitch_bit_exact(dd, B, H, W):
+    views, _ = so.synthetic_scene_batch(B, H, W, map_hw=4, seed=11)
+    ref = so.stitch(views)
+    out = dd.stitch(views.cuda())
+    assert torch.equal(out.cpu(), ref)
+    # tuple input (collate_fn form), zero-copy and copying variants
+    vc = views.cuda()
+    assert torch.equal(dd.stitch(tuple(vc.unbind(0))).cpu(), ref)
+    assert torch.equal(dd.stitch(tuple(t.clone() for t in vc.unbind(0))).cpu(), ref)
+
+
+@pytest.mark.parametrize("slot", [0, 2, 4, 5])
+def test_stitch_mask_bit_exact(dd, slot):
+    views, _ = so.synthetic_scene_batch(2, 16, 20, map_hw=4, seed=12)
+    xr, yr = so.six_to_one(views, slot)
+    x, y = dd.stitch_mask(views.cuda(), slot)
+    assert torch.equal(x.cpu(), xr) and torch.equal(y.cpu(), yr)
+
+
+def test_stitch_u8_matches_to_tensor(dd):
+    g = torch.Generator().manual_seed(1)
+    u8 = torch.randint(0, 256, (2, 6, 3, 9, 10), dtype=torch.uint8, generator=g)
+    ref = so.stitch(u8.float() / 255)
+    assert torch.equal(dd.stitch_u8(u8.cuda()).cpu(), ref)
+
+
+def test_stitch_empty_batch(dd):
+    out = dd.stitch(torch.zeros(0, 6, 3, 4, 6, device="cuda"))
+    assert out.shape == (0, 3, 4, 36)
+
+
+# ------------------------------------------------------------------------------- convs -------
+def _conv_inputs(B, H, W, seed, cin=32):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = (torch.rand(32, cin, 3, 3, generator=g) * 2 - 1) / (cin * 9) ** 0.5
+    b = (torch.rand(32, generator=g) * 2 - 1) * 0.1
+    return x, w, b
+
+
+def _call_conv_fwd(dd, x, w, b, dtype, stride, impl=1):
+    from driving_dirty_b200._lib import call, dtype_code, stream_ptr
+    B, _, H, W = x.shape
+    xin = nhwc(x, dtype)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty(B, Ho, Wo, 32, dtype=dtype, device="cuda")
+    wc, bc = w.cuda(), b.cuda()
+    call("dd_conv3x3_c32_fwd", xin.data_ptr(), wc.data_ptr(), bc.data_ptr(), out.data_ptr(), dtype_code(dtype),
+         B, H, W, stride, impl, stream_ptr())
+    return to_nchw(out)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("B,H,W,stride", [(2, 16, 120, 1), (2, 16, 120, 2), (1, 10, 84, 2), (1, 9, 35, 1),
+                                           (1, 7, 33, 2), (1, 64, 200, 1)])
+def test_conv3x3_fwd_simt(dd, dtype, tol, B, H, W, stride):
+    x, w, b = _conv_inputs(B, H, W, seed=20 + H)
+    ref = F.relu(F.conv2d(q(x, dtype), w, b, stride=stride, padding=1))
+    out = _call_conv_fwd(dd, x, w, b, dtype, stride)
+    assert rel_max_err(out, ref) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("B,H,W,stride", [(2, 16, 120, 1), (2, 16, 120, 2), (1, 10, 84, 2), (1, 9, 35, 1),
+                                           (1, 7, 33, 2), (1, 9, 35, 2)])
+def test_conv3x3_dgrad_wgrad_simt(dd, dtype, tol, B, H, W, stride):
+    from driving_dirty_b200._lib import call, dtype_code, load, stream_ptr
+    x, w, b = _conv_inputs(B, H, W, seed=40 + H)
+    x = F.relu(x)                      # the layer input is a post-ReLU activation
+    xq = q(x, dtype).requires_grad_(True)
+    wq = w.clone().requires_grad_(True)
+    bq = b.clone().requires_grad_(True)
+    y = F.conv2d(xq, wq, bq, stride=stride, padding=1)
+    g = torch.Generator().manual_seed(5)
+    dy = q(torch.randn(y.shape, generator=g), dtype)
+    y.backward(dy)
+    dx_ref = xq.grad * (xq.detach() > 0)          # mask by the input activation (previous ReLU)
+    code, st = dtype_code(dtype), stream_ptr()
+    xin, dyin = nhwc(x, dtype), nhwc(dy, dtype)
+    dx = torch.empty_like(xin)
+    wc = w.cuda()
+    call("dd_conv3x3_c32_dgrad", dyin.data_ptr(), wc.data_ptr(), xin.data_ptr(), dx.data_ptr(), code, B, H, W,
+         stride, 1, st)
+    assert rel_max_err(to_nchw(dx), dx_ref) < tol
+    # no-mask variant
+    call("dd_conv3x3_c32_dgrad", dyin.data_ptr(), wc.data_ptr(), None, dx.data_ptr(), code, B, H, W, stride, 1, st)
+    assert rel_max_err(to_nchw(dx), xq.grad) < tol
+    n = int(load().dd_conv_wgrad_workspace_bytes())
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dw, db = torch.empty(32, 32, 3, 3, device="cuda"), torch.empty(32, device="cuda")
+    call("dd_conv3x3_c32_wgrad", xin.data_ptr(), dyin.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n,
+         code, B, H, W, stride, 1, st)
+    assert rel_max_err(dw, wq.grad) < tol
+    assert rel_max_err(db, bq.grad) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("B,H,W", [(2, 16, 20), (1, 10, 14), (1, 33, 7)])
+def test_conv_c1_fwd_and_wgrad(dd, dtype, tol, B, H, W):
+    from driving_dirty_b200._lib import call, dtype_code, load, stream_ptr
+    views, _ = so.synthetic_scene_batch(B, H, W, map_hw=4, seed=31)
+    _, w, b = _conv_inputs(1, 4, 4, seed=32, cin=3)
+    mosaic = so.stitch(views)
+    wq, bq = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = F.relu(F.conv2d(mosaic, wq, bq, padding=1))
+    code, st = dtype_code(dtype), stream_ptr()
+    Wm = 6 * W
+    wc, bc = w.cuda(), b.cuda()
+    outs = []
+    for is_views, src in ((1, views.cuda()), (0, mosaic.cuda())):
+        out = torch.empty(B, H, Wm, 32, dtype=dtype, device="cuda")
+        call("dd_conv_c1_fwd", src.data_ptr(), is_views, wc.data_ptr(), bc.data_ptr(), out.data_ptr(), code, B, H, Wm, st)
+        assert rel_max_err(to_nchw(out), y) < tol
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])     # folding the stitch changes nothing
+    g = torch.Generator().manual_seed(6)
+    dy = q(torch.randn(y.shape, generator=g), dtype) * (y.detach() > 0)
+    y.backward(dy)
+    n = int(load().dd_conv_wgrad_workspace_bytes())
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dyin = nhwc(dy, dtype)
+    for is_views, src in ((1, views.cuda()), (0, mosaic.cuda())):
+        dw, db = torch.empty(32, 3, 3, 3, device="cuda"), torch.empty(32, device="cuda")
+        call("dd_conv_c1_wgrad", src.data_ptr(), is_views, dyin.data_ptr(), code, dw.data_ptr(), db.data_ptr(),
+             ws.data_ptr(), n, B, H, Wm, st)
+        assert rel_max_err(dw, wq.grad) < tol
+        assert rel_max_err(db, bq.grad) < tol
+
+
+# ------------------------------------------------------------------------------- pool --------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W", [(2, 8, 60), (2, 5, 42), (1, 3, 7), (1, 128, 918)])
+def test_pool4_fwd_bwd_exact(dd, dtype, B, H, W):
+    from driving_dirty_b200._lib import call, dtype_code, stream_ptr
+    g = torch.Generator().manual_seed(50)
+    a3 = q(F.relu(torch.randn(B, 32, H, W, generator=g)), dtype)
+    ref = so.pool4_flat(a3)
+    code, st = dtype_code(dtype), stream_ptr()
+    a3d = nhwc(a3, dtype)
+    n_out = (32 * H * W) // 4
+    pooled = torch.empty(B, n_out, dtype=dtype, device="cuda")
+    call("dd_pool4_fwd", a3d.data_ptr(), pooled.data_ptr(), code, B, H, W, st)
+    assert torch.equal(pooled.float().cpu(), ref)          # max of stored values: exact in any dtype
+    # backward: route to the FIRST max, times relu'(a3)
+    a3r = a3.clone().requires_grad_(True)
+    p = F.max_pool1d(F.relu(a3r).reshape(B, -1).unsqueeze(1), 4).squeeze(1)
+    dp = q(torch.randn(p.shape, generator=g), dtype)
+    p.backward(dp)
+    da3 = torch.empty_like(a3d)
+    dpd = dp.to(dtype).cuda()
+    call("dd_pool4_bwd", a3d.data_ptr(), dpd.data_ptr(), da3.data_ptr(), code, B, H, W, st)
+    assert torch.equal(to_nchw(da3), a3r.grad)
+
+
+def test_layout_round_trip(dd):
+    from driving_dirty_b200._lib import call, stream_ptr
+    x = torch.randn(2, 32, 5, 7)
+    xd = x.cuda()
+    nh = torch.empty(2, 5, 7, 32, device="cuda")
+    call("dd_nchw_f32_to_nhwc", xd.data_ptr(), nh.data_ptr(), 0, 2, 32, 5, 7, stream_ptr())
+    assert torch.equal(nh.cpu(), x.permute(0, 2, 3, 1).contiguous())
+    back = torch.empty_like(xd)
+    call("dd_nhwc_to_nchw_f32", nh.data_ptr(), 0, back.data_ptr(), 2, 32, 5, 7, stream_ptr())
+    assert torch.equal(back.cpu(), x)
+
+
+# ------------------------------------------------------------------------------- linear ------
+@pytest.mark.parametrize("xdtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, FP32_TOL)])
+@pytest.mark.parametrize("B,N,K", [(3, 16, 3840), (32, 256, 8192), (5, 5000, 8), (32, 4096, 128), (2, 24, 1680),
+                                    (40, 64, 1024), (1, 7, 12), (8, 130, 2052)])
+def test_linear_fwd_dgrad_wgrad(dd, xdtype, tol, B, N, K):
+    g = torch.Generator().manual_seed(60 + B)
+    x = q(torch.randn(B, K, generator=g), xdtype).requires_grad_(True)
+    w = ((torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5).requires_grad_(True)
+    b = ((torch.rand(N, generator=g) * 2 - 1) * 0.1).requires_grad_(True)
+    y = F.linear(x, w, b)
+    dy = torch.randn(B, N, generator=g)
+    y.backward(dy)
+    xd = x.detach().to(xdtype).cuda().requires_grad_(True)
+    wd = w.detach().cuda().requires_grad_(True)
+    bd = b.detach().cuda().requires_grad_(True)
+    yd = dd.linear(xd, wd, bd, impl=1)
+    assert rel_max_err(yd, y) < tol
+    yd.backward(dy.cuda())
+    # dx is stored in the activation dtype
+    assert rel_max_err(xd.grad, x.grad) < (tol if xdtype == torch.float32 else BF16_TOL)
+    assert rel_max_err(wd.grad, w.grad) < tol
+    assert rel_max_err(bd.grad, b.grad) < tol
+
+
+# ------------------------------------------------------------------------------- loss / TS ---
+def _ref_loss_bundle(logits, target):
+    probs = torch.sigmoid(logits)
+    return dict(loss=F.binary_cross_entropy_with_logits(logits.view(logits.shape[0], -1),
+                                                        target.view(target.shape[0], -1)),
+                probs=probs, binary=probs.round(), ts=so.threat_score(target, probs),
+                ts_r=so.threat_score(target, probs.round()))
+
+
+@pytest.mark.parametrize("shape", [(2, 800, 800), (3, 37, 41), (1, 1, 5), (26, 800, 800)])
+@pytest.mark.parametrize("u8", [False, True])
+def test_bce_threat_forward_backward(dd, shape, u8):
+    g = torch.Generator().manual_seed(70)
+    logits = torch.randn(shape, generator=g) * 0.06          # the scale random-init logits have
+    flat = logits.view(-1)
+    flat[:: 97] = 0.0
+    flat[1:: 89] *= 1e-6                                      # crowd the binarise threshold
+    target_b = torch.rand(shape, generator=g) > 0.5
+    target = target_b.float()
+    ref = _ref_loss_bundle(logits, target)
+    ld = logits.cuda().requires_grad_(True)
+    loss, probs, binary, stats, counts = dd.bce_threat(ld, target_b.cuda() if u8 else target.cuda())
+    assert abs(float(loss) - float(ref["loss"])) < 1e-6 * max(1.0, abs(float(ref["loss"])))
+    assert rel_max_err(probs, ref["probs"]) < 1e-6
+    assert torch.equal(binary.cpu().float(), ref["binary"])             # bit-exact binarisation
+    tp, nt, nr = so.threat_score_counts(target, ref["binary"])
+    assert counts.cpu().tolist() == [nt, nr, tp, logits.numel()]        # exact integer counts
+    assert float(stats[2]) == float(ref["ts_r"])                        # bit-exact rounded TS (<= 26 scenes)
+    assert abs(float(stats[1]) - float(ref["ts"])) < 2e-6
+    lr = logits.clone().requires_grad_(True)
+    F.binary_cross_entropy_with_logits(lr.view(shape[0], -1), target.view(shape[0], -1)).backward()
+    (loss * 1.0).backward()
+    assert rel_max_err(ld.grad, lr.grad) < 1e-6
+    assert rel_max_err(ld.grad, so.bce_with_logits_grad(logits, target)) < 1e-6
+
+
+def test_binarise_exhaustive_sweep(dd, golden):
+    """Every fp32 in [2^-27, 2^-20): the kernel's binary map equals the reference's
+    sigmoid().round() (goldens: first 1 at bits 0x33C00001), plus the edge cases."""
+    gold = golden("binarise")
+    bits = np.arange(gold["sweep_lo"], gold["sweep_hi"], dtype=np.uint32)
+    n = (len(bits) // 4) * 4
+    x = torch.from_numpy(bits[:n].view(np.float32).copy())
+    _, binary = dd.sigmoid_binary(x.cuda())
+    got = binary.cpu()
+    first = int(torch.nonzero(got).flatten()[0])
+    assert int(bits[first]) == gold["first_one_bits"]
+    assert bool((got[first:] == 1).all()) and bool((got[:first] == 0).all())
+    e = gold["edge_x"]
+    e = torch.cat([e, e[:2]])[:16]
+    p, b = dd.sigmoid_binary(e.cuda())
+    assert torch.equal(b.cpu().float()[:14], gold["edge_round"])
+    assert rel_max_err(p.cpu()[:12], gold["edge_sigmoid"][:12]) < 1e-6
+    # negatives never binarise to 1
+    _, bn = dd.sigmoid_binary((-x[: 1 << 20]).cuda())
+    assert int(bn.sum()) == 0
+
+
+def test_threat_score_and_mse(dd):
+    g = torch.Generator().manual_seed(80)
+    a, b = torch.rand(3, 100, 100, generator=g), (torch.rand(3, 100, 100, generator=g) > 0.5).float()
+    assert abs(float(dd.threat_score(a.cuda(), b.cuda())) - float(so.threat_score(a, b))) < 1e-6
+    z = torch.zeros(4, 4)
+    assert torch.isnan(dd.threat_score(z.cuda(), z.cuda()))             # 0/0 like the reference
+    y, yh = torch.randn(2, 3, 16, 20, generator=g), torch.randn(2, 3, 16, 20, generator=g)
+    yhd = yh.cuda().requires_grad_(True)
+    yhr = yh.clone().requires_grad_(True)
+    lr = F.mse_loss(y, yhr)
+    lr.backward()
+    ld = dd.mse_loss(y.cuda(), yhd)
+    ld.backward()
+    assert abs(float(ld) - float(lr)) < 1e-6 and rel_max_err(yhd.grad, yhr.grad) < 1e-6

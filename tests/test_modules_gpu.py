@@ -1,0 +1,179 @@
+"""Module-level parity on the GPU: the drop-in RoadMapBCE / ModelLoader (calling the C ABI)
+against the CPU oracle and the golden vectors written from the unmodified reference."""
+import pytest
+import torch
+
+from oracle import scene_oracle as so
+from tests.helpers import build_roadmap_pair, cpu_rng_dropout, make_roadmap_model, rel_max_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _load_case(golden, name, dtype="fp32"):
+    g = golden(name)
+    model, params, views, road = build_roadmap_pair(g["batch"], g["hidden"], g["latent"], g["view_h"], g["view_w"],
+                                                    dtype=dtype, seed_w=g["seed_w"], seed_x=g["seed_x"])
+    return g, model, params, views, road
+
+
+def _flips(binary, ref_logits):
+    """pixels whose binarisation differs from the reference, and the largest |reference logit|
+    among them (only logits within ~1e-7 of the threshold may flip on the fp32 path)"""
+    ref_bin = so.binarise(ref_logits, from_logits=True)
+    diff = binary.float().cpu() != ref_bin
+    return int(diff.sum()), float(ref_logits[diff].abs().max()) if diff.any() else 0.0
+
+
+@pytest.mark.parametrize("name", ["roadmap_small", "roadmap_odd"])
+def test_eval_pass_fp32_against_golden(golden, name):
+    g, model, params, views, road = _load_case(golden, name)
+    e = g["eval"]
+    batch = (tuple(views.cuda().unbind(0)), None, tuple(road.cuda().unbind(0)))
+    with torch.no_grad(), cpu_rng_dropout():
+        assert so.strided_sample(model.wide_stitch_six_images(batch[0]).cpu()).equal(e["mosaic_sample"])
+        torch.manual_seed(g["seed_fwd"])
+        loss, target_rm, logits, probs = model._run_step(batch, 1, "valid")
+        torch.manual_seed(g["seed_fwd"])
+        ref = so.run_step(params, views, road, training=False)
+    scale = e["logits_absmax"]
+    assert float((so.strided_sample(logits.cpu()) - e["logits_sample"]).abs().max()) / scale < 1e-5
+    assert rel_max_err(logits, ref["logits"]) < 1e-5
+    assert abs(float(loss) - float(e["loss"])) < 1e-5
+    assert rel_max_err(probs, ref["probs"]) < 1e-5
+    m = model.last_metrics
+    nflip, worst = _flips(m["binary"], ref["logits"])
+    assert worst < 1e-6, f"{nflip} flipped pixels, largest |logit| {worst}"
+    assert abs(float(m["ts_rounded"]) - float(e["ts_rounded"])) <= 4e-7 * max(nflip, 1)
+    assert abs(float(m["ts"]) - float(e["ts"])) < 1e-5
+    # forward() returns (logits, probs) and is the same computation
+    with torch.no_grad(), cpu_rng_dropout():
+        torch.manual_seed(g["seed_fwd"])
+        y, p = model(batch[0])
+    assert torch.equal(y, logits) and rel_max_err(p, probs) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["roadmap_small", "roadmap_odd"])
+def test_binarise_and_ts_bit_exact_on_reference_logits(golden, name):
+    """Fed the reference's own logits, the fused kernel reproduces its binary map and rounded
+    threat score bit for bit (golden sha / value)."""
+    import hashlib
+    import numpy as np
+    from driving_dirty_b200 import ops
+    g = golden(name)
+    p = so.init_roadmap_params(g["hidden"], g["latent"], g["view_h"], g["view_w"], seed=g["seed_w"])
+    views, road = so.synthetic_scene_batch(g["batch"], g["view_h"], g["view_w"], seed=g["seed_x"])
+    with torch.no_grad():
+        ref = so.run_step(p, views, road, training=False, seed=g["seed_fwd"])
+    loss, probs, binary, stats, counts = ops.bce_threat(ref["logits"].cuda(), road.cuda())
+    sha = hashlib.sha256(np.ascontiguousarray(binary.cpu().numpy())).hexdigest()
+    assert sha == g["eval"]["binary_sha"]
+    assert int(counts[1]) == g["eval"]["binary_ones"]
+    assert float(stats[2]) == float(g["eval"]["ts_rounded"])
+    assert abs(float(loss) - float(g["eval"]["loss"])) < 1e-6
+
+
+@pytest.mark.parametrize("name,dtype,tol", [("roadmap_small", "fp32", 1e-5), ("roadmap_odd", "fp32", 1e-5),
+                                            ("roadmap_small", "bf16", 1e-2), ("roadmap_odd", "bf16", 1e-2)])
+def test_train_pass_gradients(golden, name, dtype, tol):
+    g, model, params, views, road = _load_case(golden, name, dtype)
+    t = g["train"]
+    batch = (tuple(views.cuda().unbind(0)), None, tuple(road.cuda().unbind(0)))
+    with cpu_rng_dropout():
+        torch.manual_seed(g["seed_fwd"])
+        out = model.training_step(batch, 1)          # unfreezes at epoch 0 like the reference
+        out["loss"].backward()
+        ref, grads = so.train_step_grads(params, views, road, seed=g["seed_fwd"])
+    assert not model.frozen and model.ae.encoder.c2.weight.requires_grad
+    assert abs(float(out["loss"]) - float(t["loss"])) < (1e-5 if dtype == "fp32" else 1e-3)
+    named = dict(model.named_parameters())
+    assert sorted(named) == sorted(t["grad_norm"])
+    for k, p in named.items():
+        assert p.grad is not None, k
+        ref_g = grads[k]
+        # fp32: relative to max|ref| per tensor; bf16: relative Frobenius (activations are stored in bf16)
+        if dtype == "fp32":
+            assert rel_max_err(p.grad, ref_g) < 2e-5, k
+            assert float((so.strided_sample(p.grad.cpu(), 2048) - t["grad_sample"][k]).abs().max()) \
+                <= 2e-5 * float(ref_g.abs().max()) + 1e-12, k
+        else:
+            num = float((p.grad.cpu().double() - ref_g.double()).norm())
+            assert num / max(float(ref_g.double().norm()), 1e-30) < 3e-2, k
+    # BatchNorm running statistics moved exactly like the reference's
+    sd = model.state_dict()
+    for k, v in t["bn_after"].items():
+        if v.is_floating_point():
+            assert rel_max_err(sd[k], v) < (1e-5 if dtype == "fp32" else 2e-2), k
+        else:
+            assert int(sd[k]) == int(v), k
+
+
+def test_full_size_eval_fp32(golden):
+    """BASELINE config 1 shapes on the GPU: B=2, views 6x3x256x306, hidden 256 / latent 128."""
+    g, model, params, views, road = _load_case(golden, "roadmap_full_b2")
+    e = g["eval"]
+    batch = (tuple(views.cuda().unbind(0)), None, tuple(road.cuda().unbind(0)))
+    with torch.no_grad(), cpu_rng_dropout():
+        torch.manual_seed(g["seed_fwd"])
+        loss, _, logits, probs = model._run_step(batch, 1, "valid")
+    err = float((so.strided_sample(logits.cpu()) - e["logits_sample"]).abs().max()) / e["logits_absmax"]
+    assert err < 1e-5, err
+    assert abs(float(loss) - float(e["loss"])) < 1e-5
+    assert abs(float(model.last_metrics["ts_rounded"]) - float(e["ts_rounded"])) < 1e-5
+    assert abs(int(model.last_metrics["counts"][1]) - e["binary_ones"]) <= 8
+
+
+def test_full_size_train_bf16_vs_fp32_golden(golden):
+    """bf16 tensor-core path at full size against the reference's fp32 gradients (1e-2 contract,
+    relative Frobenius per tensor)."""
+    g, model, params, views, road = _load_case(golden, "roadmap_full_b2", dtype="bf16")
+    t = g["train"]
+    batch = (tuple(views.cuda().unbind(0)), None, tuple(road.cuda().unbind(0)))
+    with cpu_rng_dropout():
+        torch.manual_seed(g["seed_fwd"])
+        out = model.training_step(batch, 1)
+        out["loss"].backward()
+    assert abs(float(out["loss"]) - float(t["loss"])) < 1e-3
+    for k, p in model.named_parameters():
+        got = float(p.grad.double().norm())
+        assert abs(got - t["grad_norm"][k]) <= 3e-2 * t["grad_norm"][k] + 1e-12, (k, got, t["grad_norm"][k])
+        s = so.strided_sample(p.grad.cpu(), 2048)
+        ref_s = t["grad_sample"][k]
+        assert float((s - ref_s).norm()) <= 5e-2 * float(ref_s.norm()) + 1e-12, k
+
+
+def test_model_loader_binary_road_map(golden):
+    from driving_dirty_b200.model_loader import ModelLoader
+    g, model, params, views, road = _load_case(golden, "roadmap_small")
+    loader = ModelLoader(model)
+    with cpu_rng_dropout():
+        torch.manual_seed(g["seed_fwd"])
+        rm = loader.get_binary_road_map(views.cuda())
+        torch.manual_seed(g["seed_fwd"])
+        with torch.no_grad():
+            ref = so.run_step(params, views, road, training=False)
+    assert rm.shape == (g["batch"], 800, 800) and rm.dtype == torch.float32 and rm.is_cuda
+    assert set(rm.unique().tolist()) <= {0.0, 1.0}
+    nflip, worst = _flips(rm, ref["logits"])
+    assert worst < 1e-6
+    boxes = loader.get_bounding_boxes(views.cuda())
+    assert len(boxes) == g["batch"] and boxes[0].shape[1:] == (2, 4)
+    from driving_dirty_b200.utils.helper import compute_ts_road_map
+    ts = compute_ts_road_map(road.float().cuda(), rm)
+    assert abs(float(ts) - float(g["eval"]["ts_rounded"])) < 1e-5
+
+
+def test_encoder_mosaic_entry_and_c3_only(golden):
+    """Encoder.forward(mosaic) == forward_views(views); c3_only returns the NCHW c3 activation."""
+    g, model, params, views, road = _load_case(golden, "roadmap_small")
+    enc = model.ae.encoder
+    with torch.no_grad(), cpu_rng_dropout():
+        torch.manual_seed(3)
+        z1 = enc(model.wide_stitch_six_images(views.cuda()))
+        torch.manual_seed(3)
+        z2 = enc.forward_views(views.cuda())
+        assert torch.equal(z1, z2)
+        enc.c3_only = True
+        ssr = enc(model.wide_stitch_six_images(views.cuda()))
+        enc.c3_only = False
+    _, _, a3 = so.encoder_convs(params, so.stitch(views))
+    assert ssr.shape == a3.shape and rel_max_err(ssr, a3) < 1e-5
