@@ -1,11 +1,274 @@
-// tcgen05 / TMEM implicit-GEMM convolutions (bf16) -- placeholder until the kernels land.
+// 32->32 3x3 convolutions of the encoder as implicit GEMMs on the 5th-gen tensor cores
+// (tcgen05.mma, accumulators in TMEM), bf16 NHWC activations, fp32 accumulate.
+// Reference ops: components.py:20-21,42-43 (c2, c3) and their input gradients.
+//
+// Formulation ("row marching"): a CTA owns a strip of 128 output pixels of one image and walks
+// down ROWS output rows.  GEMM per output row:  D[128 pix x 32 co] = sum over 9 taps of
+// A_tap[128 pix x 32 ci] * W_tap[32 ci x 32 co]  -> 18 tcgen05.mma (M=128, N=32, K=16) into one
+// 32-column TMEM accumulator.
+//
+// Shared-memory layout of an input row ("slab"): four channel-group planes, each [pixel][8 ch] =
+// 16 B per pixel (core matrices of the SWIZZLE_NONE K-major canonical layout: 8 pixels x 16 B).
+// Because the layout is unswizzled, the A operand of tap kw is the SAME slab addressed kw*16 B
+// further on: every input row is loaded ONCE per strip and reused by 9 taps / 3 output rows
+// (verified on hardware by tools/umma_probe.cu, profiles/r1_umma_descriptor_probe.txt).
+// Stride 2 keeps even and odd input pixels in separate planes so that consecutive output pixels
+// still read consecutive 16-byte rows.
+//
+// Warp roles (192 threads): warp 0 = producer (cp.async 16 B, zero-fill = conv padding),
+// warp 1 = MMA issuer (one lane) + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU or
+// ReLU-mask -> bf16 -> global).  mbarrier rings: slab full/empty (8 deep), accumulator
+// full/empty (4 x 32 TMEM columns), so loads, MMAs and epilogues of different rows overlap.
 #include "dd_common.cuh"
-namespace dd {
-bool conv_tc_supported(int, int, int, int) { return false; }
-int conv3x3_c32_fwd_tc(const void*, const float*, const float*, void*, int, int, int, int, int, const void*, cudaStream_t) {
-  return fail(DD_ERR_UNSUPPORTED, "tcgen05 conv not built");
+#include "umma.cuh"
+
+namespace {
+
+constexpr int C = 32;
+constexpr int TILE_M = 128;
+constexpr int ROWS = 32;            // output rows per work item
+constexpr int RING = 8;             // slab ring depth
+constexpr int INFLIGHT = 4;         // cp.async groups in flight before the oldest is published
+constexpr int NACC = 4;             // TMEM accumulator buffers (32 columns each)
+constexpr int NPAD = 136;           // pixels per plane (>= 130, and 129 per parity plane for stride 2)
+constexpr int PS = NPAD * 16;       // plane stride in bytes
+constexpr int W_BYTES = 9 * 4 * 512;  // bf16 weights [tap][cg][co][8 ci]
+constexpr int NTHREADS = 192;
+
+template <int STRIDE>
+struct Geo {
+  static constexpr int NPIX = (TILE_M - 1) * STRIDE + 3;      // input pixels per slab: 130 / 257
+  static constexpr int PLANES = 4 * STRIDE;                   // stride 2: even + odd pixel planes
+  static constexpr int SLAB_BYTES = PLANES * PS;
+  static constexpr int SMEM = W_BYTES + RING * SLAB_BYTES + 1024;
+};
+
+struct Bars {
+  uint64_t full[RING], empty[RING], acc_full[NACC], acc_empty[NACC];
+  uint32_t tmem_base;
+};
+
+// MODE 0: forward (bias + ReLU).  MODE 1: stride-1 input gradient (flipped/transposed filter,
+// epilogue multiplies by mask > 0).
+template <int STRIDE, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                      const float* __restrict__ w_oihw,
+                                                                      const float* __restrict__ bias,
+                                                                      const __nv_bfloat16* __restrict__ mask,
+                                                                      __nv_bfloat16* __restrict__ out, int B, int H,
+                                                                      int W, int Ho, int Wo) {
+  using G = Geo<STRIDE>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_slab = smem + W_BYTES;
+  Bars* bars = reinterpret_cast<Bars*>(smem + W_BYTES + RING * G::SLAB_BYTES);
+  __shared__ float s_bias[C];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wtiles = (Wo + TILE_M - 1) / TILE_M;
+  const int hsegs = (Ho + ROWS - 1) / ROWS;
+  const int items = B * wtiles * hsegs;
+
+  // ---- one-time setup: weights -> bf16 UMMA layout, barriers, TMEM ---------------------------
+  for (int i = tid; i < 9 * C * C; i += NTHREADS) {
+    const int ci = i & 31, co = (i >> 5) & 31, tap = i >> 10;     // (in-channel role, out-channel role)
+    float v;
+    if (MODE == 0) v = w_oihw[(co * C + ci) * 9 + tap];
+    else v = w_oihw[(ci * C + co) * 9 + (8 - tap)];               // dgrad: W[co=in][ci=out][flipped tap]
+    *reinterpret_cast<__nv_bfloat16*>(s_w + (tap * 4 + (ci >> 3)) * 512 + co * 16 + (ci & 7) * 2) = __float2bfloat16_rn(v);
+  }
+  if (tid < C) s_bias[tid] = (MODE == 0) ? bias[tid] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 4); }
+    umma::fence_mbar_init();
+  }
+  if (warp == 1) umma::tmem_alloc(&bars->tmem_base, NACC * 32);
+  umma::fence_proxy_async_smem();      // weights were written with generic stores
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // =========================== producer ======================================================
+    uint32_t g = 0;                      // global slab counter
+    uint32_t published = 0;              // slabs whose full barrier has been signalled
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int ho0 = hs * ROWS;
+      const int rows = min(ROWS, Ho - ho0);
+      const int nslabs = (rows - 1) * STRIDE + 3;
+      const int r0 = ho0 * STRIDE - 1;                 // first input row
+      const int c0 = wt * TILE_M * STRIDE - 1;         // first input column
+      const __nv_bfloat16* img = in + (size_t)b * H * W * C;
+      for (int s = 0; s < nslabs; ++s, ++g) {
+        const uint32_t slot = g % RING;
+        umma::mbar_wait(&bars->empty[slot], ((g / RING) & 1) ^ 1);
+        const int r = r0 + s;
+        const bool row_ok = (r >= 0) && (r < H);
+        const uint32_t dst0 = umma::smem_u32(s_slab + slot * G::SLAB_BYTES);
+        const __nv_bfloat16* rowp = img + (size_t)(row_ok ? r : 0) * W * C;
+        for (int c = lane; c < G::NPIX * 4; c += 32) {
+          const int li = c >> 2, cg = c & 3;
+          const int col = c0 + li;
+          const bool ok = row_ok && (col >= 0) && (col < W);
+          uint32_t dst;
+          if (STRIDE == 1) dst = dst0 + cg * PS + li * 16;
+          else dst = dst0 + ((li & 1) * 4 + cg) * PS + (li >> 1) * 16;
+          umma::cp_async16(dst, rowp + (size_t)(ok ? col : 0) * C + cg * 8, ok ? 16u : 0u);
+        }
+        umma::cp_async_commit();
+        if (g + 1 - published >= INFLIGHT) {           // publish the oldest in-flight slab
+          umma::cp_async_wait<INFLIGHT - 1>();
+          umma::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(&bars->full[published % RING]);
+          ++published;
+        }
+      }
+    }
+    umma::cp_async_wait<0>();
+    umma::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0)
+      for (; published < g; ++published) umma::mbar_arrive(&bars->full[published % RING]);
+  } else if (warp == 1) {
+    // =========================== MMA issuer ====================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma::make_idesc_bf16(TILE_M, C, false, false);
+      const uint32_t wbase = umma::smem_u32(s_w);
+      const uint32_t sbase = umma::smem_u32(s_slab);
+      uint32_t g0 = 0;            // slab counter at the start of the current item
+      uint32_t waited = 0;        // slabs [0, waited) are known to be full
+      uint32_t row_ctr = 0;       // global output-row counter (accumulator ring)
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int hs = (it / wtiles) % hsegs;
+        const int rows = min(ROWS, Ho - hs * ROWS);
+        const int nslabs = (rows - 1) * STRIDE + 3;
+        for (int j = 0; j < rows; ++j, ++row_ctr) {
+          const uint32_t need = g0 + j * STRIDE + 3;
+          for (; waited < need; ++waited) umma::mbar_wait(&bars->full[waited % RING], (waited / RING) & 1);
+          const uint32_t buf = row_ctr % NACC;
+          umma::mbar_wait(&bars->acc_empty[buf], ((row_ctr / NACC) & 1) ^ 1);
+          umma::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem + buf * 32;
+          uint32_t first = 1;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t slab = sbase + ((g0 + j * STRIDE + kh) % RING) * G::SLAB_BYTES;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              uint32_t a_off;
+              if (STRIDE == 1) a_off = kw * 16;
+              else a_off = (kw == 1 ? 4 * PS : 0) + (kw == 2 ? 16 : 0);    // kw: 0 -> even[i], 1 -> odd[i], 2 -> even[i+1]
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t da = umma::make_desc(slab + a_off + (2 * ks) * PS, PS, 128);
+                const uint64_t db = umma::make_desc(wbase + ((kh * 3 + kw) * 4 + 2 * ks) * 512, 512, 128);
+                umma::mma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+          }
+          umma::mma_commit(&bars->acc_full[buf]);
+          // input rows that no later output row of this item reads
+          const int nrel = (j == rows - 1) ? 3 : STRIDE;
+          for (int q = 0; q < nrel; ++q) umma::mma_commit(&bars->empty[(g0 + j * STRIDE + q) % RING]);
+        }
+        g0 += nslabs;
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) =========================================
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
+    uint32_t row_ctr = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int ho0 = hs * ROWS;
+      const int rows = min(ROWS, Ho - ho0);
+      const int wo = wt * TILE_M + quarter * 32 + lane;
+      for (int j = 0; j < rows; ++j, ++row_ctr) {
+        const uint32_t buf = row_ctr % NACC;
+        umma::mbar_wait(&bars->acc_full[buf], (row_ctr / NACC) & 1);
+        umma::tc_fence_after_sync();
+        uint32_t r[32];
+        umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * 32, r);
+        umma::tmem_ld_wait();
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bars->acc_empty[buf]);
+        if (wo < Wo) {
+          const size_t off = (((size_t)b * Ho + ho0 + j) * Wo + wo) * C;
+          float v[C];
+#pragma unroll
+          for (int k = 0; k < C; ++k) v[k] = __uint_as_float(r[k]);
+          if (MODE == 0) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) v[k] = fmaxf(v[k] + s_bias[k], 0.f);
+          } else if (mask) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              float m[8];
+              dd::ld8<__nv_bfloat16>(mask + off + gq * 8, m);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[gq * 8 + k] = m[k] > 0.f ? v[gq * 8 + k] : 0.f;
+            }
+          }
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            float t8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t8[k] = v[gq * 8 + k];
+            dd::st8<__nv_bfloat16>(out + off + gq * 8, t8);
+          }
+        }
+      }
+    }
+  }
+  // ---- teardown ---------------------------------------------------------------------------------
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem, NACC * 32);
 }
+
+template <int STRIDE, int MODE>
+int launch(const void* in, const float* w, const float* bias, const void* mask, void* out, int B, int H, int W,
+           cudaStream_t st) {
+  using G = Geo<STRIDE>;
+  const int Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
+  const int items = B * ((Wo + TILE_M - 1) / TILE_M) * ((Ho + ROWS - 1) / ROWS);
+  auto k = conv3x3_c32_tc_kernel<STRIDE, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+  if (e != cudaSuccess) return dd::fail((int)e, "conv_tc: cudaFuncSetAttribute(%d): %s", G::SMEM, cudaGetErrorString(e));
+  const int grid = items < dd::kSMs ? items : dd::kSMs;
+  k<<<grid, NTHREADS, G::SMEM, st>>>((const __nv_bfloat16*)in, w, bias, (const __nv_bfloat16*)mask,
+                                     (__nv_bfloat16*)out, B, H, W, Ho, Wo);
+  return dd::check_launch("conv3x3_c32_tc");
+}
+
+}  // namespace
+
+namespace dd {
+
+// mode: 0 forward, 1 input gradient, 2 weight gradient
+bool conv_tc_supported(int H, int W, int stride, int mode) {
+  if (H < 1 || W < 1) return false;
+  if (mode == 0) return stride == 1 || stride == 2;
+  if (mode == 1) return stride == 1;
+  return false;
+}
+
+int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int stride,
+                       int mode, const void* mask, cudaStream_t st) {
+  if (mode == 0 && stride == 1) return launch<1, 0>(in, w, bias, nullptr, out, B, H, W, st);
+  if (mode == 0 && stride == 2) return launch<2, 0>(in, w, bias, nullptr, out, B, H, W, st);
+  if (mode == 1 && stride == 1) return launch<1, 1>(in, w, nullptr, mask, out, B, H, W, st);
+  return fail(DD_ERR_UNSUPPORTED, "conv_tc: mode %d stride %d", mode, stride);
+}
+
 int conv3x3_c32_wgrad_tc(const void*, const void*, float*, float*, void*, size_t, int, int, int, int, cudaStream_t) {
   return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad not built");
 }
+
 }  // namespace dd

@@ -83,9 +83,9 @@ int launch_stitch(const float* views, float* x, float* y, int B, int H, int W, i
 }  // namespace
 
 extern "C" int dd_stitch_f32(const float* views, float* mosaic, int B, int H, int W, void* stream) {
-  DD_REQUIRE(views && mosaic, DD_ERR_BAD_ARG, "dd_stitch_f32: null pointer");
   DD_REQUIRE(B >= 0 && H > 0 && W > 0, DD_ERR_BAD_ARG, "dd_stitch_f32: bad shape B=%d H=%d W=%d", B, H, W);
-  if (B == 0) return 0;
+  if (B == 0) return 0;   // empty batch: nothing to move (torch hands out null pointers for empty tensors)
+  DD_REQUIRE(views && mosaic, DD_ERR_BAD_ARG, "dd_stitch_f32: null pointer");
   return launch_stitch(views, mosaic, nullptr, B, H, W, -1, 0, dd::as_stream(stream));
 }
 

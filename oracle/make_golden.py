@@ -70,11 +70,18 @@ def roadmap_case(name: str, batch: int, hidden: int, latent: int, view_h: int, v
     seed_w, seed_x, seed_fwd = 20200505, 20200506, 1234
     params = so.init_roadmap_params(hidden, latent, view_h, view_w, seed=seed_w)
     views, road = so.synthetic_scene_batch(batch, view_h, view_w, seed=seed_x)
+    if store_params:
+        # small train cases: pick the first input seed with no conv pre-activation within 2e-6 of the
+        # ReLU threshold (see scene_oracle.min_abs_preactivation)
+        while so.min_abs_preactivation(params, views) < 2e-6:
+            seed_x += 1
+            views, road = so.synthetic_scene_batch(batch, view_h, view_w, seed=seed_x)
     model = build_reference_roadmap(params, hidden, latent, view_h, view_w)
     sample_t = tuple(views.unbind(0))   # what collate_fn hands the module (helper.py:22-23)
     road_t = tuple(road.unbind(0))
     gold = dict(name=name, batch=batch, hidden=hidden, latent=latent, view_h=view_h, view_w=view_w,
-                seed_w=seed_w, seed_x=seed_x, seed_fwd=seed_fwd)
+                seed_w=seed_w, seed_x=seed_x, seed_fwd=seed_fwd,
+                min_abs_preactivation=so.min_abs_preactivation(params, views))
 
     # ---- frozen / eval pass (validation_step, roadmap_bce_v2.py:135-143) -------------------
     with torch.no_grad():
@@ -177,9 +184,9 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     binarise_case()
-    roadmap_case("roadmap_small", batch=3, hidden=16, latent=8, view_h=16, view_w=20,
+    roadmap_case("roadmap_small", batch=4, hidden=16, latent=8, view_h=16, view_w=20,
                  with_grads=True, store_params=True)
-    roadmap_case("roadmap_odd", batch=2, hidden=24, latent=8, view_h=10, view_w=14,
+    roadmap_case("roadmap_odd", batch=5, hidden=24, latent=8, view_h=10, view_w=14,
                  with_grads=True, store_params=True)
     ae_case("ae_small", batch=3, hidden=16, latent=8, view_h=16, view_w=20)
     ae_case("ae_stitch_full", batch=2, hidden=8, latent=8, view_h=256, view_w=306)

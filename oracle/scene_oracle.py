@@ -65,11 +65,42 @@ def six_to_one(views: torch.Tensor, target_slot: int):
 # ----------------------------------------------------------------------------------------
 # A3 / A4 / A5: encoder convs and the flat max-pool
 # ----------------------------------------------------------------------------------------
-def encoder_convs(p: dict, x: torch.Tensor, prefix: str = "ae.encoder."):
-    """components.py:41-43: relu(c1), relu(c2), relu(c3 stride 2), all 3x3 pad 1."""
-    a1 = F.relu(F.conv2d(x, p[prefix + "c1.weight"], p[prefix + "c1.bias"], padding=1))
-    a2 = F.relu(F.conv2d(a1, p[prefix + "c2.weight"], p[prefix + "c2.bias"], padding=1))
-    a3 = F.relu(F.conv2d(a2, p[prefix + "c3.weight"], p[prefix + "c3.bias"], stride=2, padding=1))
+class _StoreAs(torch.autograd.Function):
+    """Emulates a tensor being STORED in a narrower dtype on both passes: forward rounds the
+    activation to ``dtype``, backward rounds the gradient arriving at it.  Used only for the
+    like-for-like check of the bf16 activation-storage path (the fp32 oracle never calls it)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        return x.to(dtype).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype).float(), None
+
+
+def _store(x, dtype):
+    return x if dtype is None or dtype == torch.float32 else _StoreAs.apply(x, dtype)
+
+
+def _weight_as(w, dtype):
+    """Operand rounding of a weight (tensor-core path reads conv weights as bf16); gradients pass
+    straight through to the fp32 master weight."""
+    if dtype is None or dtype == torch.float32:
+        return w
+    return w + (w.detach().to(dtype).float() - w.detach())
+
+
+def encoder_convs(p: dict, x: torch.Tensor, prefix: str = "ae.encoder.", act_dtype=None, weight_dtype=None):
+    """components.py:41-43: relu(c1), relu(c2), relu(c3 stride 2), all 3x3 pad 1.
+    ``act_dtype`` / ``weight_dtype`` (default None = the reference's fp32) emulate the storage
+    rounding points of the bf16 path: a1, a2, a3 and their gradients; c2/c3 weights as operands."""
+    a1 = _store(F.relu(F.conv2d(x, p[prefix + "c1.weight"], p[prefix + "c1.bias"], padding=1)), act_dtype)
+    a2 = _store(F.relu(F.conv2d(a1, _weight_as(p[prefix + "c2.weight"], weight_dtype), p[prefix + "c2.bias"],
+                                padding=1)), act_dtype)
+    a3 = _store(F.relu(F.conv2d(a2, _weight_as(p[prefix + "c3.weight"], weight_dtype), p[prefix + "c3.bias"],
+                                stride=2, padding=1)), act_dtype)
     return a1, a2, a3
 
 
@@ -111,15 +142,16 @@ def dense_block(p: dict, prefix: str, x: torch.Tensor, training: bool, drop_p: f
 
 
 def encoder_forward(p: dict, x: torch.Tensor, training: bool, prefix: str = "ae.encoder.",
-                    c3_only: bool = False) -> torch.Tensor:
+                    c3_only: bool = False, act_dtype=None, weight_dtype=None) -> torch.Tensor:
     """components.py:40-52 (Encoder.forward)."""
-    _, _, a3 = encoder_convs(p, x, prefix)
+    _, _, a3 = encoder_convs(p, x, prefix, act_dtype, weight_dtype)
     if c3_only:  # components.py:44-45
         return a3
     # components.py:46-47.  F.max_pool1d (not amax) so that autograd routes the gradient to the
     # FIRST maximum of each window like the reference; pool4_flat() above is the index-level
     # restatement and tests check the two agree.
     pooled = F.max_pool1d(a3.reshape(a3.shape[0], -1).unsqueeze(1), kernel_size=4).squeeze(1)
+    pooled = _store(pooled, act_dtype)   # no-op on the values; rounds d(pooled) on the way back
     h = dense_block(p, prefix + "fc1.", pooled, training)
     h = dense_block(p, prefix + "fc2.", h, training)
     return F.linear(h, p[prefix + "fc_z_out.weight"], p[prefix + "fc_z_out.bias"])
@@ -128,14 +160,14 @@ def encoder_forward(p: dict, x: torch.Tensor, training: bool, prefix: str = "ae.
 # ----------------------------------------------------------------------------------------
 # A8-A11: roadmap head, loss, binarise, threat score
 # ----------------------------------------------------------------------------------------
-def roadmap_forward(p: dict, views, training: bool, map_hw: int = 800):
+def roadmap_forward(p: dict, views, training: bool, map_hw: int = 800, act_dtype=None, weight_dtype=None):
     """roadmap_bce_v2.py:66-81: stitch -> encoder -> Linear(latent, 800*800) -> reshape;
     returns (logits, sigmoid(logits)).  ``views`` may be a [B,6,3,H,W] tensor or the
     collate_fn tuple of [6,3,H,W] tensors (roadmap_bce_v2.py:55 stacks it)."""
     if not torch.is_tensor(views):
         views = torch.stack(tuple(views), dim=0)
     x = stitch(views)
-    z = encoder_forward(p, x, training)
+    z = encoder_forward(p, x, training, act_dtype=act_dtype, weight_dtype=weight_dtype)
     y = F.linear(z, p["fc1.weight"], p["fc1.bias"]).reshape(z.shape[0], map_hw, map_hw)
     return y, torch.sigmoid(y)
 
@@ -184,7 +216,8 @@ def threat_score_counts(target01: torch.Tensor, pred01: torch.Tensor):
     return int((t * r).sum()), int(t.sum()), int(r.sum())
 
 
-def run_step(p: dict, views, road_image, training: bool, seed: int | None = None):
+def run_step(p: dict, views, road_image, training: bool, seed: int | None = None, act_dtype=None,
+             weight_dtype=None):
     """roadmap_bce_v2.py:83-108 (_run_step) + :135-143 (validation_step metrics).
 
     Returns dict(loss, logits, probs, ts, ts_rounded).  ``seed`` re-seeds the torch RNG just
@@ -195,14 +228,15 @@ def run_step(p: dict, views, road_image, training: bool, seed: int | None = None
     target = road_image.float()  # :87
     if seed is not None:
         torch.manual_seed(seed)
-    logits, probs = roadmap_forward(p, views, training, map_hw=target.shape[-1])
+    logits, probs = roadmap_forward(p, views, training, map_hw=target.shape[-1], act_dtype=act_dtype,
+                                    weight_dtype=weight_dtype)
     b = target.shape[0]
     loss = F.binary_cross_entropy_with_logits(logits.view(b, -1), target.view(b, -1))  # :106
     return dict(loss=loss, logits=logits, probs=probs, target=target,
                 ts=threat_score(target, probs), ts_rounded=threat_score(target, probs.round()))
 
 
-def train_step_grads(p: dict, views, road_image, seed: int, names=None):
+def train_step_grads(p: dict, views, road_image, seed: int, names=None, act_dtype=None, weight_dtype=None):
     """fwd + BCE + backward through the restated path with torch autograd on CPU (what
     loss.backward() does in the reference after unfreeze(), roadmap_bce_v2.py:125-133).
     Returns (out dict, {name: grad})."""
@@ -214,7 +248,7 @@ def train_step_grads(p: dict, views, road_image, seed: int, names=None):
     for k in p:
         if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
             q[k] = p[k].clone()
-    out = run_step(q, views, road_image, training=True, seed=seed)
+    out = run_step(q, views, road_image, training=True, seed=seed, act_dtype=act_dtype, weight_dtype=weight_dtype)
     out["loss"].backward()
     return out, {k: q[k].grad for k in names}
 
@@ -255,6 +289,21 @@ def strided_sample(t: torch.Tensor, n: int = 4096) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------
 # synthetic inputs / weights shared by tests, smoke() and bench.py
 # ----------------------------------------------------------------------------------------
+def min_abs_preactivation(p: dict, views: torch.Tensor, prefix: str = "ae.encoder.") -> float:
+    """Smallest |pre-activation| over the three encoder convs.  An fp32 implementation that sums in
+    a different order can flip relu'(x) for |x| ~ 1e-7, which moves every upstream gradient by a
+    whole pixel's contribution; golden train cases are chosen so that this value is > 2e-6 and the
+    1e-5 gradient contract is testable (make_golden.py searches the input seed)."""
+    x = stitch(views)
+    m = float("inf")
+    strides = {"c1": 1, "c2": 1, "c3": 2}
+    for name in ("c1", "c2", "c3"):
+        pre = F.conv2d(x, p[prefix + name + ".weight"], p[prefix + name + ".bias"], stride=strides[name], padding=1)
+        m = min(m, float(pre.abs().min()))
+        x = F.relu(pre)
+    return m
+
+
 def synthetic_scene_batch(batch: int, view_h: int = 256, view_w: int = 306, map_hw: int = 800,
                           seed: int = 20200505):
     g = torch.Generator().manual_seed(seed)

@@ -3,12 +3,12 @@
 # the rest), module tests, smoke, short bench.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-for k in stitch conv3x3_fwd dgrad_wgrad conv_c1 pool4 layout linear bce_threat binarise threat_score; do
+for k in tcgen05 stitch conv3x3_fwd_simt dgrad_wgrad conv_c1 pool4 layout linear bce_threat binarise threat_score; do
   echo "=== $k" >> gpurun_out/tests.log
   timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "$k" -x 2>&1 | tail -25 >> gpurun_out/tests.log
 done
 echo "=== modules" >> gpurun_out/tests.log
-timeout 900 python -m pytest tests/test_modules_gpu.py -m gpu -q 2>&1 | tail -60 >> gpurun_out/tests.log
+timeout 900 python -m pytest tests/test_modules_gpu.py -m gpu -q -s 2>&1 | grep -v Warning | tail -150 >> gpurun_out/tests.log
 echo "=== smoke" >> gpurun_out/tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" >> gpurun_out/tests.log 2>&1
 echo "=== bench" >> gpurun_out/tests.log

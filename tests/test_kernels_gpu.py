@@ -99,6 +99,46 @@ def test_conv3x3_fwd_simt(dd, dtype, tol, B, H, W, stride):
     assert rel_max_err(out, ref) < tol
 
 
+TC_SHAPES = [(2, 16, 120, 1), (2, 16, 120, 2), (1, 10, 84, 2), (1, 9, 35, 1), (1, 7, 33, 2), (1, 64, 200, 1),
+             (1, 70, 300, 2), (2, 256, 1836, 1), (2, 256, 1836, 2), (1, 40, 129, 1), (1, 33, 257, 2)]
+
+
+@pytest.mark.parametrize("B,H,W,stride", TC_SHAPES)
+def test_conv3x3_fwd_tcgen05(dd, B, H, W, stride):
+    """tcgen05/TMEM implicit-GEMM forward (bf16 operands, fp32 accumulate) against the oracle conv on
+    the same bf16-rounded inputs and weights; the full-size cases run 240 work items over 148 CTAs
+    (persistent loop, slab-ring and accumulator-ring wrap-around)."""
+    x, w, b = _conv_inputs(B, H, W, seed=20 + H)
+    ref = F.relu(F.conv2d(q(x, torch.bfloat16), q(w, torch.bfloat16), b, stride=stride, padding=1))
+    out = _call_conv_fwd(dd, x, w, b, torch.bfloat16, stride, impl=2)
+    assert rel_max_err(out, ref) < 5e-3      # one bf16 rounding of the output
+    simt = _call_conv_fwd(dd, x, w, b, torch.bfloat16, stride, impl=1)
+    assert rel_max_err(out, simt) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 120), (1, 9, 35), (1, 64, 200), (2, 256, 1836), (1, 40, 129)])
+def test_conv3x3_dgrad_tcgen05(dd, B, H, W):
+    from driving_dirty_b200._lib import call, dtype_code, stream_ptr
+    dtype = torch.bfloat16
+    x, w, b = _conv_inputs(B, H, W, seed=40 + H)
+    x = F.relu(x)
+    xq = q(x, dtype).requires_grad_(True)
+    y = F.conv2d(xq, q(w, dtype), None, stride=1, padding=1)
+    g = torch.Generator().manual_seed(5)
+    dy = q(torch.randn(y.shape, generator=g), dtype)
+    y.backward(dy)
+    dx_ref = xq.grad * (xq.detach() > 0)
+    xin, dyin = nhwc(x, dtype), nhwc(dy, dtype)
+    dx = torch.empty_like(xin)
+    wc = w.cuda()
+    call("dd_conv3x3_c32_dgrad", dyin.data_ptr(), wc.data_ptr(), xin.data_ptr(), dx.data_ptr(), dtype_code(dtype),
+         B, H, W, 1, 2, stream_ptr())
+    assert rel_max_err(to_nchw(dx), dx_ref) < 5e-3
+    call("dd_conv3x3_c32_dgrad", dyin.data_ptr(), wc.data_ptr(), None, dx.data_ptr(), dtype_code(dtype),
+         B, H, W, 1, 2, stream_ptr())
+    assert rel_max_err(to_nchw(dx), xq.grad) < 5e-3
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
 @pytest.mark.parametrize("B,H,W,stride", [(2, 16, 120, 1), (2, 16, 120, 2), (1, 10, 84, 2), (1, 9, 35, 1),
                                            (1, 7, 33, 2), (1, 9, 35, 2)])
