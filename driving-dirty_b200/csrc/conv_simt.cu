@@ -427,7 +427,7 @@ __global__ void relu_mask_kernel(const T* __restrict__ g, const T* __restrict__ 
 }
 
 constexpr int kWgradBlocks = dd::kSMs * 2;
-constexpr size_t kWgradWsBytes = (size_t)kWgradBlocks * (9 * C * C + C) * sizeof(float);
+constexpr size_t kWgradWsBytes = (size_t)12 << 20;   // >= SIMT partials (296 x 9248 floats) and tcgen05 partials (148 x 18432 + 592 x 32)
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {

@@ -247,6 +247,191 @@ int launch(const void* in, const float* w, const float* bias, const void* mask, 
   return dd::check_launch("conv3x3_c32_tc");
 }
 
+
+// ================================================================================================
+// Weight gradient on the tensor cores (stride 1):
+//   dW[co][ci][kh][kw] = sum_{b,h,w} x[b,h+kh-1,w+kw-1,ci] * dy[b,h,w,co]
+// The contraction runs over PIXELS, so both operands are MN-major: A = x planes (M = 4 input rows x
+// 32 ci = 128), B = dy planes (N = 2 dy rows x 32 co = 64), K = 16 pixels per tcgen05.mma.  For the
+// dy-row pair (h, h+1) and x rows h-1..h+2, block (r, q) of D holds tap kh = r - q; 6 of the 8
+// blocks are useful.  kw is again a 16-byte shift of the A start address, one 64-column TMEM
+// accumulator per kw, accumulated over every work item of the CTA and written out ONCE at the end
+// as [cta][q][tap][ci][co] partials that an ordered reduction kernel folds (deterministic).
+// Stage = 4 dy rows + 6 x rows of a 128-pixel column strip, double buffered; warps 0,1,3 are
+// cp.async producers, warp 2 issues the MMAs, all four warps run the final epilogue.
+// ================================================================================================
+constexpr int WG_ROWS = 4;                       // dy rows per stage
+constexpr int WG_XROWS = WG_ROWS + 2;
+constexpr int PSD = TILE_M * 16;                 // dy plane stride (128 pixels)
+constexpr int WG_X_BYTES = WG_XROWS * 4 * PS;
+constexpr int WG_DY_BYTES = WG_ROWS * 4 * PSD;
+constexpr int WG_STAGE_BYTES = WG_X_BYTES + WG_DY_BYTES;
+constexpr int WG_SMEM = 2 * WG_STAGE_BYTES + 1024;
+constexpr int WG_PARTIAL = 2 * 9 * C * C;        // floats per CTA
+
+struct WgBars {
+  uint64_t full[2], empty[2], done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(128, 1) conv3x3_c32_wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                       const __nv_bfloat16* __restrict__ dy,
+                                                                       float* __restrict__ partial, int B, int H,
+                                                                       int W) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WgBars* bars = reinterpret_cast<WgBars*>(smem + 2 * WG_STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wtiles = (W + TILE_M - 1) / TILE_M;
+  const int hsegs = (H + WG_ROWS - 1) / WG_ROWS;
+  const int items = B * wtiles * hsegs;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->full[i], 3); umma::mbar_init(&bars->empty[i], 1); }
+    umma::mbar_init(&bars->done, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 2) umma::tmem_alloc(&bars->tmem_base, 256);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp != 2) {
+    // =========================== producers (warps 0, 1, 3) =====================================
+    const int pl = (warp == 3 ? 2 : warp) * 32 + lane;      // 0..95
+    uint32_t n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int h0 = hs * WG_ROWS, w0 = wt * TILE_M;
+      const uint32_t stage = n & 1;
+      umma::mbar_wait(&bars->empty[stage], ((n >> 1) & 1) ^ 1);
+      const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
+      const uint32_t ds = xs + WG_X_BYTES;
+      const __nv_bfloat16* ximg = x + (size_t)b * H * W * C;
+      const __nv_bfloat16* dimg = dy + (size_t)b * H * W * C;
+      constexpr int XCH = WG_XROWS * 130 * 4;
+      for (int c = pl; c < XCH; c += 96) {
+        const int cg = c & 3, t = c >> 2;
+        const int r = t / 130, li = t - r * 130;
+        const int row = h0 - 1 + r, col = w0 - 1 + li;
+        const bool ok = row >= 0 && row < H && col >= 0 && col < W;
+        umma::cp_async16(xs + (r * 4 + cg) * PS + li * 16,
+                         ximg + ((size_t)(ok ? row : 0) * W + (ok ? col : 0)) * C + cg * 8, ok ? 16u : 0u);
+      }
+      constexpr int DCH = WG_ROWS * TILE_M * 4;
+      for (int c = pl; c < DCH; c += 96) {
+        const int cg = c & 3, t = c >> 2;
+        const int r = t >> 7, li = t & 127;
+        const int row = h0 + r, col = w0 + li;
+        const bool ok = row < H && col < W;
+        umma::cp_async16(ds + (r * 4 + cg) * PSD + li * 16,
+                         dimg + ((size_t)(ok ? row : 0) * W + (ok ? col : 0)) * C + cg * 8, ok ? 16u : 0u);
+      }
+      umma::cp_async_commit();
+      umma::cp_async_wait<0>();
+      umma::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&bars->full[stage]);
+    }
+  } else if (lane == 0) {
+    // =========================== MMA issuer ====================================================
+    constexpr uint32_t idesc = umma::make_idesc_bf16(128, 64, true, true);
+    uint32_t n = 0;
+    uint32_t fresh = 1;     // accumulators not yet written
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const uint32_t stage = n & 1;
+      umma::mbar_wait(&bars->full[stage], (n >> 1) & 1);
+      umma::tc_fence_after_sync();
+      const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
+      const uint32_t ds = xs + WG_X_BYTES;
+#pragma unroll
+      for (int p = 0; p < WG_ROWS / 2; ++p) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+          for (int ks = 0; ks < TILE_M / 16; ++ks) {
+            const uint64_t da = umma::make_desc(xs + (2 * p * 4) * PS + kw * 16 + ks * 256, 128, PS);
+            const uint64_t db = umma::make_desc(ds + (2 * p * 4) * PSD + ks * 256, 128, PSD);
+            umma::mma_bf16(tmem + kw * 64, da, db, idesc, (fresh && p == 0 && ks == 0) ? 0u : 1u);
+          }
+        }
+      }
+      fresh = 0;
+      umma::mma_commit(&bars->empty[stage]);
+    }
+    umma::mma_commit(&bars->done);
+  }
+  // =========================== epilogue: TMEM -> per-CTA partials ================================
+  __syncwarp();
+  umma::mbar_wait(&bars->done, 0);
+  umma::tc_fence_after_sync();
+  {
+    const int r = warp;                      // TMEM lane quarter = x row offset r; lane = ci
+    float* out = partial + (size_t)blockIdx.x * WG_PARTIAL;
+#pragma unroll 1
+    for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        uint32_t v[32];
+        umma::tmem_ld_32x32(tmem + ((uint32_t)(r * 32) << 16) + kw * 64 + q * 32, v);
+        umma::tmem_ld_wait();
+        const int kh = r - q;
+        if (kh >= 0 && kh <= 2) {
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)q * 9 * C * C + ((kh * 3 + kw) * C + lane) * C);
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4)
+            dst[g4] = make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]),
+                                  __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
+        }
+      }
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) umma::tmem_dealloc(tmem, 256);
+}
+
+// per-channel sums of an NHWC bf16 tensor (bias gradient): partial[blk][32]
+__global__ void __launch_bounds__(256) colsum_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long npix,
+                                                               float* __restrict__ partial) {
+  __shared__ float red[64][33];
+  const int cg = threadIdx.x & 3, pl = threadIdx.x >> 2;     // 64 pixel lanes x 4 channel groups
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long p = (long long)blockIdx.x * 64 + pl; p < npix; p += (long long)gridDim.x * 64) {
+    float v[8];
+    dd::ld8<__nv_bfloat16>(dy + p * C + cg * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[pl][cg * 8 + k] = s[k];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+    for (int i = 0; i < 64; ++i) t += red[i][threadIdx.x];
+    partial[(size_t)blockIdx.x * C + threadIdx.x] = t;
+  }
+}
+
+// dw[co][ci][tap] = sum over CTAs and the two q slots; db[co] = sum over colsum CTAs
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ dbp,
+                                       int ndb, float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 9 * C * C) {
+    float s = 0.f;
+    for (int blk = 0; blk < 2 * nblk; ++blk) s += partial[(size_t)blk * (9 * C * C) + i];
+    const int co = i & 31, ci = (i >> 5) & 31, tap = i >> 10;
+    dw[(co * C + ci) * 9 + tap] = s;
+  } else if (i < 9 * C * C + C) {
+    const int co = i - 9 * C * C;
+    float s = 0.f;
+    for (int blk = 0; blk < ndb; ++blk) s += dbp[(size_t)blk * C + co];
+    db[co] = s;
+  }
+}
+
+constexpr int kDbBlocks = dd::kSMs * 4;
+
 }  // namespace
 
 namespace dd {
@@ -256,6 +441,7 @@ bool conv_tc_supported(int H, int W, int stride, int mode) {
   if (H < 1 || W < 1) return false;
   if (mode == 0) return stride == 1 || stride == 2;
   if (mode == 1) return stride == 1;
+  if (mode == 2) return stride == 1;
   return false;
 }
 
@@ -267,8 +453,25 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
   return fail(DD_ERR_UNSUPPORTED, "conv_tc: mode %d stride %d", mode, stride);
 }
 
-int conv3x3_c32_wgrad_tc(const void*, const void*, float*, float*, void*, size_t, int, int, int, int, cudaStream_t) {
-  return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad not built");
+int conv3x3_c32_wgrad_tc(const void* x, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int B, int H,
+                         int W, int stride, cudaStream_t st) {
+  if (stride != 1) return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: stride %d", stride);
+  const int items = B * ((W + TILE_M - 1) / TILE_M) * ((H + WG_ROWS - 1) / WG_ROWS);
+  const int grid = items < kSMs ? items : kSMs;
+  const size_t need = ((size_t)grid * WG_PARTIAL + (size_t)kDbBlocks * C) * sizeof(float);
+  if (ws_bytes < need) return fail(DD_ERR_WORKSPACE, "tcgen05 wgrad: workspace %zu < %zu", ws_bytes, need);
+  float* partial = (float*)ws;
+  float* dbp = partial + (size_t)grid * WG_PARTIAL;
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+  if (e != cudaSuccess) return fail((int)e, "wgrad_tc: cudaFuncSetAttribute(%d): %s", WG_SMEM, cudaGetErrorString(e));
+  conv3x3_c32_wgrad_tc_kernel<<<grid, 128, WG_SMEM, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, B, H, W);
+  if (int err = check_launch("conv3x3_c32_wgrad_tc")) return err;
+  const long long npix = (long long)B * H * W;
+  const int dbg = (int)((npix + 63) / 64 < kDbBlocks ? (npix + 63) / 64 : kDbBlocks);
+  colsum_nhwc_bf16_kernel<<<dbg, 256, 0, st>>>((const __nv_bfloat16*)dy, npix, dbp);
+  if (int err = check_launch("colsum_nhwc_bf16")) return err;
+  wgrad_tc_reduce_kernel<<<(9 * C * C + C + 255) / 256, 256, 0, st>>>(partial, grid, dbp, dbg, dw, db);
+  return check_launch("wgrad_tc_reduce");
 }
 
 }  // namespace dd
