@@ -116,14 +116,16 @@ def test_conv3x3_fwd_tcgen05(dd, B, H, W, stride):
     assert rel_max_err(out, simt) < BF16_TOL
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 16, 120), (1, 9, 35), (1, 64, 200), (2, 256, 1836), (1, 40, 129)])
-def test_conv3x3_dgrad_tcgen05(dd, B, H, W):
+@pytest.mark.parametrize("B,H,W,stride", [(2, 16, 120, 1), (1, 9, 35, 1), (1, 64, 200, 1), (2, 256, 1836, 1),
+                                           (1, 40, 129, 1), (2, 16, 120, 2), (1, 9, 35, 2), (1, 10, 84, 2),
+                                           (1, 64, 515, 2), (2, 256, 1836, 2), (1, 33, 258, 2)])
+def test_conv3x3_dgrad_tcgen05(dd, B, H, W, stride):
     from driving_dirty_b200._lib import call, dtype_code, stream_ptr
     dtype = torch.bfloat16
     x, w, b = _conv_inputs(B, H, W, seed=40 + H)
     x = F.relu(x)
     xq = q(x, dtype).requires_grad_(True)
-    y = F.conv2d(xq, q(w, dtype), None, stride=1, padding=1)
+    y = F.conv2d(xq, q(w, dtype), None, stride=stride, padding=1)
     g = torch.Generator().manual_seed(5)
     dy = q(torch.randn(y.shape, generator=g), dtype)
     y.backward(dy)
@@ -132,15 +134,17 @@ def test_conv3x3_dgrad_tcgen05(dd, B, H, W):
     dx = torch.empty_like(xin)
     wc = w.cuda()
     call("dd_conv3x3_c32_dgrad", dyin.data_ptr(), wc.data_ptr(), xin.data_ptr(), dx.data_ptr(), dtype_code(dtype),
-         B, H, W, 1, 2, stream_ptr())
+         B, H, W, stride, 2, stream_ptr())
     assert rel_max_err(to_nchw(dx), dx_ref) < 5e-3
     call("dd_conv3x3_c32_dgrad", dyin.data_ptr(), wc.data_ptr(), None, dx.data_ptr(), dtype_code(dtype),
-         B, H, W, 1, 2, stream_ptr())
+         B, H, W, stride, 2, stream_ptr())
     assert rel_max_err(to_nchw(dx), xq.grad) < 5e-3
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 16, 120), (1, 9, 35), (1, 64, 200), (2, 256, 1836), (1, 40, 129), (3, 5, 131)])
-def test_conv3x3_wgrad_tcgen05(dd, B, H, W):
+@pytest.mark.parametrize("B,H,W,stride", [(2, 16, 120, 1), (1, 9, 35, 1), (1, 64, 200, 1), (2, 256, 1836, 1),
+                                           (1, 40, 129, 1), (3, 5, 131, 1), (2, 16, 120, 2), (1, 9, 35, 2),
+                                           (1, 10, 84, 2), (1, 64, 515, 2), (2, 256, 1836, 2), (3, 5, 131, 2)])
+def test_conv3x3_wgrad_tcgen05(dd, B, H, W, stride):
     """tcgen05 weight gradient (pixels as the contraction axis, MN-major operands) against autograd on
     the same bf16-rounded x / dy; fp32 accumulation, deterministic ordered reduction."""
     from driving_dirty_b200._lib import call, dtype_code, load, stream_ptr
@@ -148,7 +152,7 @@ def test_conv3x3_wgrad_tcgen05(dd, B, H, W):
     x, w, b = _conv_inputs(B, H, W, seed=40 + H)
     xq = q(F.relu(x), dtype)
     wq, bq = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    y = F.conv2d(xq, wq, bq, stride=1, padding=1)
+    y = F.conv2d(xq, wq, bq, stride=stride, padding=1)
     g = torch.Generator().manual_seed(5)
     dy = q(torch.randn(y.shape, generator=g), dtype)
     y.backward(dy)
@@ -159,7 +163,7 @@ def test_conv3x3_wgrad_tcgen05(dd, B, H, W):
     for _ in range(2):
         dw, db = torch.empty(32, 32, 3, 3, device="cuda"), torch.empty(32, device="cuda")
         call("dd_conv3x3_c32_wgrad", xin.data_ptr(), dyin.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n,
-             dtype_code(dtype), B, H, W, 1, 2, stream_ptr())
+             dtype_code(dtype), B, H, W, stride, 2, stream_ptr())
         outs.append((dw.clone(), db.clone()))
     assert rel_max_err(outs[0][0], wq.grad) < 2e-4
     assert rel_max_err(outs[0][1], bq.grad) < 2e-4
