@@ -152,10 +152,8 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def build_model(dtype: str, device):
-    from tests.helpers import make_roadmap_model
-    from oracle import scene_oracle as so   # only for the deterministic synthetic weights / scenes
-    params = so.init_roadmap_params(HIDDEN, LATENT, VIEW_H, VIEW_W)
-    model = make_roadmap_model(params, HIDDEN, LATENT, VIEW_H, VIEW_W, dtype=dtype, device=device)
+    from driving_dirty_b200.synthetic import random_roadmap_model
+    model = random_roadmap_model(HIDDEN, LATENT, VIEW_H, VIEW_W, dtype=dtype, device=device)
     model.frozen = False
     model.ae.unfreeze()
     model.train()
@@ -243,7 +241,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from driving_dirty_b200 import _lib
     from driving_dirty_b200.distributed import GradAllReducer
-    from oracle import scene_oracle as so
+    from driving_dirty_b200.synthetic import scene_batch
 
     B = args.batch
     model = build_model(args.dtype, dev)
@@ -252,7 +250,7 @@ def run_ours(args):
     reducer = GradAllReducer(params)
 
     # synthetic scenes: a different batch per rank, pinned on the host, one resident copy in HBM
-    views_h, road_h = so.synthetic_scene_batch(B, VIEW_H, VIEW_W, seed=20200506 + rank)
+    views_h, road_h = scene_batch(B, VIEW_H, VIEW_W, seed=20200506 + rank)
     views_h, road_h = views_h.pin_memory(), road_h.pin_memory()
     views_d, road_d = views_h.to(dev, non_blocking=True), road_h.to(dev, non_blocking=True)
 

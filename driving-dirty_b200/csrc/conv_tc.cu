@@ -15,11 +15,14 @@
 // Stride 2 keeps even and odd input pixels in separate planes so that consecutive output pixels
 // still read consecutive 16-byte rows.
 //
-// Warp roles (192 threads): warp 0 = producer (cp.async 16 B, zero-fill = conv padding),
-// warp 1 = MMA issuer (one lane) + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU or
+// Warp roles (288 threads): warps 0..3 = producers (cp.async 16 B, zero-fill = conv padding; one
+// warp cannot issue the ~520 copies per input row fast enough -- ncu showed the MMA thread starved),
+// warp 4 = MMA issuer (one lane) + TMEM owner, warps 5..8 = epilogue (tcgen05.ld -> bias/ReLU or
 // ReLU-mask -> bf16 -> global).  mbarrier rings: slab full/empty (8 deep), accumulator
 // full/empty (4 x 32 TMEM columns), so loads, MMAs and epilogues of different rows overlap.
 #include "dd_common.cuh"
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace {
@@ -28,12 +31,13 @@ constexpr int C = 32;
 constexpr int TILE_M = 128;
 constexpr int ROWS = 32;            // output rows per work item
 constexpr int RING = 8;             // slab ring depth
-constexpr int INFLIGHT = 4;         // cp.async groups in flight before the oldest is published
 constexpr int NACC = 4;             // TMEM accumulator buffers (32 columns each)
 constexpr int NPAD = 136;           // pixels per plane (>= 130, and 129 per parity plane for stride 2)
 constexpr int PS = NPAD * 16;       // plane stride in bytes
 constexpr int W_BYTES = 9 * 4 * 512;  // bf16 weights [tap][cg][co][8 ci]
-constexpr int NTHREADS = 192;
+constexpr int NPROD = 4;             // producer warps (0..3); warp 4 issues MMAs; warps 5..8 run the epilogue
+constexpr int MMA_WARP = NPROD;
+constexpr int NTHREADS = 32 * (NPROD + 1 + 4);
 
 template <int STRIDE>
 struct Geo {
@@ -42,6 +46,41 @@ struct Geo {
   static constexpr int SLAB_BYTES = PLANES * PS;
   static constexpr int SMEM = W_BYTES + RING * SLAB_BYTES + 1024;
 };
+
+// Epilogue-side wait: back off between polls so the spinning warps do not take issue slots from the
+// producer / MMA warps that share their schedulers.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!umma::mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
+// One input row -> slab planes, by NT cooperating threads.  Thread (cg = ptid & 3, lp = ptid >> 2)
+// copies pixels lp, lp+NT/4, ...: source and destination advance by constants, only the bounds
+// predicate varies.  PPL > 0: stride-2 layout, odd pixels live PPL planes after the even ones.
+template <int NPIX, int PPL, int PLANE_STRIDE = PS, int NT = 128>
+__device__ __forceinline__ void load_slab(uint32_t dst0, const __nv_bfloat16* __restrict__ rowp, bool row_ok, int c0,
+                                          int W, int ptid) {
+  constexpr bool PARITY_PLANES = PPL > 0;
+  constexpr int PX = NT / 4;          // pixels covered per step
+  const int cg = ptid & 3, lp = ptid >> 2;
+  uint32_t dst = PARITY_PLANES ? dst0 + ((lp & 1) * PPL + cg) * PLANE_STRIDE + (lp >> 1) * 16
+                               : dst0 + cg * PLANE_STRIDE + lp * 16;
+  const __nv_bfloat16* src = rowp + (ptrdiff_t)(c0 + lp) * C + cg * 8;
+  int col = c0 + lp;
+#pragma unroll
+  for (int k = 0; k < (NPIX + PX - 1) / PX; ++k) {
+    if ((k + 1) * PX <= NPIX || lp + k * PX < NPIX) {
+      const bool ok = row_ok && col >= 0 && col < W;
+      umma::cp_async16(dst, ok ? src : rowp, ok ? 16u : 0u);
+    }
+    dst += PARITY_PLANES ? PX * 8 : PX * 16;
+    src += PX * C;
+    col += PX;
+  }
+}
 
 struct Bars {
   uint64_t full[RING], empty[RING], acc_full[NACC], acc_empty[NACC];
@@ -56,7 +95,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
                                                                       const float* __restrict__ bias,
                                                                       const __nv_bfloat16* __restrict__ mask,
                                                                       __nv_bfloat16* __restrict__ out, int B, int H,
-                                                                      int W, int Ho, int Wo) {
+                                                                      int W, int Ho, int Wo, int dbg) {
   using G = Geo<STRIDE>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
@@ -64,7 +103,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
   Bars* bars = reinterpret_cast<Bars*>(smem + W_BYTES + RING * G::SLAB_BYTES);
   __shared__ float s_bias[C];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role code stays on the uniform datapath
   const int wtiles = (Wo + TILE_M - 1) / TILE_M;
   const int hsegs = (Ho + ROWS - 1) / ROWS;
   const int items = B * wtiles * hsegs;
@@ -79,21 +119,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
   }
   if (tid < C) s_bias[tid] = (MODE == 0) ? bias[tid] : 0.f;
   if (tid == 0) {
-    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 32); umma::mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 4); }
     umma::fence_mbar_init();
   }
-  if (warp == 1) umma::tmem_alloc(&bars->tmem_base, NACC * 32);
+  if (warp == MMA_WARP) umma::tmem_alloc(&bars->tmem_base, NACC * 32);
   umma::fence_proxy_async_smem();      // weights were written with generic stores
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
-  if (warp == 0) {
-    // =========================== producer ======================================================
+  if (warp < NPROD) {
+    // =========================== producers =====================================================
+    // Warp w owns slabs g = w (mod NPROD) and loads each of them whole; the slab's full barrier
+    // (count 32) is armed with cp.async.mbarrier.arrive.noinc, so a slab is published by the
+    // hardware when its copies land and the warp never blocks on its own loads: up to RING slabs
+    // are in flight per SM.
     uint32_t g = 0;                      // global slab counter
-    uint32_t published = 0;              // slabs whose full barrier has been signalled
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
       const int ho0 = hs * ROWS;
@@ -103,42 +146,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
       const int c0 = wt * TILE_M * STRIDE - 1;         // first input column
       const __nv_bfloat16* img = in + (size_t)b * H * W * C;
       for (int s = 0; s < nslabs; ++s, ++g) {
+        if ((g % NPROD) != (uint32_t)warp) continue;
         const uint32_t slot = g % RING;
         umma::mbar_wait(&bars->empty[slot], ((g / RING) & 1) ^ 1);
         const int r = r0 + s;
         const bool row_ok = (r >= 0) && (r < H);
-        const uint32_t dst0 = umma::smem_u32(s_slab + slot * G::SLAB_BYTES);
-        const __nv_bfloat16* rowp = img + (size_t)(row_ok ? r : 0) * W * C;
-        for (int c = lane; c < G::NPIX * 4; c += 32) {
-          const int li = c >> 2, cg = c & 3;
-          const int col = c0 + li;
-          const bool ok = row_ok && (col >= 0) && (col < W);
-          uint32_t dst;
-          if (STRIDE == 1) dst = dst0 + cg * PS + li * 16;
-          else dst = dst0 + ((li & 1) * 4 + cg) * PS + (li >> 1) * 16;
-          umma::cp_async16(dst, rowp + (size_t)(ok ? col : 0) * C + cg * 8, ok ? 16u : 0u);
-        }
-        umma::cp_async_commit();
-        if (g + 1 - published >= INFLIGHT) {           // publish the oldest in-flight slab
-          umma::cp_async_wait<INFLIGHT - 1>();
-          umma::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) umma::mbar_arrive(&bars->full[published % RING]);
-          ++published;
-        }
+        if (!(dbg & 4))
+          load_slab<G::NPIX, STRIDE == 2 ? 4 : 0, PS, 32>(umma::smem_u32(s_slab + slot * G::SLAB_BYTES),
+                                                          img + (size_t)(row_ok ? r : 0) * W * C, row_ok, c0, W, lane);
+        umma::cp_async_mbar_arrive_noinc(&bars->full[slot]);
       }
     }
-    umma::cp_async_wait<0>();
-    umma::fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0)
-      for (; published < g; ++published) umma::mbar_arrive(&bars->full[published % RING]);
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ====================================================
-    if (lane == 0) {
+    // The whole warp runs this (uniform) loop and one elected lane issues: a lone divergent thread
+    // makes ptxas shuttle every descriptor through R2UR (~90 cycles per tcgen05.mma, measured).
+    {
       constexpr uint32_t idesc = umma::make_idesc_bf16(TILE_M, C, false, false);
-      const uint32_t wbase = umma::smem_u32(s_w);
-      const uint32_t sbase = umma::smem_u32(s_slab);
+      const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), PS);     // A: LBO = plane stride, SBO = 128
+      const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), 512);       // B: LBO = 512, SBO = 128
       uint32_t g0 = 0;            // slab counter at the start of the current item
       uint32_t waited = 0;        // slabs [0, waited) are known to be full
       uint32_t row_ctr = 0;       // global output-row counter (accumulator ring)
@@ -149,38 +175,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
         for (int j = 0; j < rows; ++j, ++row_ctr) {
           const uint32_t need = g0 + j * STRIDE + 3;
           for (; waited < need; ++waited) umma::mbar_wait(&bars->full[waited % RING], (waited / RING) & 1);
+          umma::fence_proxy_async_smem();     // cp.async (generic proxy) writes -> UMMA (async proxy) reads
           const uint32_t buf = row_ctr % NACC;
           umma::mbar_wait(&bars->acc_empty[buf], ((row_ctr / NACC) & 1) ^ 1);
           umma::tc_fence_after_sync();
           const uint32_t d_tmem = tmem + buf * 32;
-          uint32_t first = 1;
+          constexpr uint32_t a_hi = umma::desc_hi(128), b_hi = umma::desc_hi(128);
+          if (!(dbg & 1) && umma::elect_one())
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t slab = sbase + ((g0 + j * STRIDE + kh) % RING) * G::SLAB_BYTES;
+            const uint32_t slab_lo = a_lo0 + ((g0 + j * STRIDE + kh) % RING) * (G::SLAB_BYTES >> 4);
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              uint32_t a_off;
-              if (STRIDE == 1) a_off = kw * 16;
-              else a_off = (kw == 1 ? 4 * PS : 0) + (kw == 2 ? 16 : 0);    // kw: 0 -> even[i], 1 -> odd[i], 2 -> even[i+1]
+              // stride 2: kw 0 -> even[i], 1 -> odd[i], 2 -> even[i+1]
+              const int a_off = STRIDE == 1 ? kw * 16 : (kw == 1 ? 4 * PS : 0) + (kw == 2 ? 16 : 0);
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t da = umma::make_desc(slab + a_off + (2 * ks) * PS, PS, 128);
-                const uint64_t db = umma::make_desc(wbase + ((kh * 3 + kw) * 4 + 2 * ks) * 512, 512, 128);
-                umma::mma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
-                first = 0;
-              }
+              for (int ks = 0; ks < 2; ++ks)
+                umma::mma_bf16_lohi(d_tmem, slab_lo + ((a_off + (2 * ks) * PS) >> 4), a_hi,
+                                    b_lo0 + (((kh * 3 + kw) * 4 + 2 * ks) * 512 >> 4), b_hi, idesc,
+                                    (kh | kw | ks) ? 1u : 0u);
             }
           }
-          umma::mma_commit(&bars->acc_full[buf]);
-          // input rows that no later output row of this item reads
-          const int nrel = (j == rows - 1) ? 3 : STRIDE;
-          for (int q = 0; q < nrel; ++q) umma::mma_commit(&bars->empty[(g0 + j * STRIDE + q) % RING]);
+          if (umma::elect_one()) {
+            umma::mma_commit(&bars->acc_full[buf]);
+            // input rows that no later output row of this item reads
+            const int nrel = (j == rows - 1) ? 3 : STRIDE;
+            for (int q = 0; q < nrel; ++q) umma::mma_commit(&bars->empty[(g0 + j * STRIDE + q) % RING]);
+          }
+          __syncwarp();
         }
         g0 += nslabs;
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) =========================================
+    // =========================== epilogue (warps 5..8) =========================================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
     uint32_t row_ctr = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -190,7 +218,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
       const int wo = wt * TILE_M + quarter * 32 + lane;
       for (int j = 0; j < rows; ++j, ++row_ctr) {
         const uint32_t buf = row_ctr % NACC;
-        umma::mbar_wait(&bars->acc_full[buf], (row_ctr / NACC) & 1);
+        const size_t off = (((size_t)b * Ho + ho0 + j) * Wo + (wo < Wo ? wo : 0)) * C;
+        uint4 mk[4];
+        if (MODE == 1 && mask != nullptr) {      // in flight while this warp waits for the MMAs
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) mk[gq] = __ldg(reinterpret_cast<const uint4*>(mask + off) + gq);
+        }
+        mbar_wait_relaxed(&bars->acc_full[buf], (row_ctr / NACC) & 1);
         umma::tc_fence_after_sync();
         uint32_t r[32];
         umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * 32, r);
@@ -198,8 +232,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
         umma::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(&bars->acc_empty[buf]);
-        if (wo < Wo) {
-          const size_t off = (((size_t)b * Ho + ho0 + j) * Wo + wo) * C;
+        if (wo < Wo && !(dbg & 2)) {
           float v[C];
 #pragma unroll
           for (int k = 0; k < C; ++k) v[k] = __uint_as_float(r[k]);
@@ -209,10 +242,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
           } else if (mask) {
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
-              float m[8];
-              dd::ld8<__nv_bfloat16>(mask + off + gq * 8, m);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&mk[gq]);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) v[gq * 8 + k] = m[k] > 0.f ? v[gq * 8 + k] : 0.f;
+              for (int k = 0; k < 4; ++k) {
+                const float2 m = __bfloat1622float2(h2[k]);
+                v[gq * 8 + 2 * k] = m.x > 0.f ? v[gq * 8 + 2 * k] : 0.f;
+                v[gq * 8 + 2 * k + 1] = m.y > 0.f ? v[gq * 8 + 2 * k + 1] : 0.f;
+              }
             }
           }
 #pragma unroll
@@ -229,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
   // ---- teardown ---------------------------------------------------------------------------------
   umma::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem, NACC * 32);
+  if (warp == MMA_WARP) umma::tmem_dealloc(tmem, NACC * 32);
 }
 
 template <int STRIDE, int MODE>
@@ -242,8 +278,9 @@ int launch(const void* in, const float* w, const float* bias, const void* mask, 
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
   if (e != cudaSuccess) return dd::fail((int)e, "conv_tc: cudaFuncSetAttribute(%d): %s", G::SMEM, cudaGetErrorString(e));
   const int grid = items < dd::kSMs ? items : dd::kSMs;
+  static const int dbg = getenv("DD_CONV_DBG") ? atoi(getenv("DD_CONV_DBG")) : 0;   // profiling aid: 1 no MMA, 2 no stores, 4 no loads
   k<<<grid, NTHREADS, G::SMEM, st>>>((const __nv_bfloat16*)in, w, bias, (const __nv_bfloat16*)mask,
-                                     (__nv_bfloat16*)out, B, H, W, Ho, Wo);
+                                     (__nv_bfloat16*)out, B, H, W, Ho, Wo, dbg);
   return dd::check_launch("conv3x3_c32_tc");
 }
 
@@ -275,7 +312,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(co
   uint8_t* s_w = smem;
   uint8_t* s_slab = smem + W_BYTES;
   DgBars* bars = reinterpret_cast<DgBars*>(smem + W_BYTES + RING * SLAB);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role code stays on the uniform datapath
   const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
   const int wtiles = (Wp + TILE_M - 1) / TILE_M;
   const int hsegs = (Hp + DG_MROWS - 1) / DG_MROWS;
@@ -288,20 +326,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(co
         __float2bfloat16_rn(w_oihw[(co * C + ci) * 9 + tap]);
   }
   if (tid == 0) {
-    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 32); umma::mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 4); }
     umma::fence_mbar_init();
   }
-  if (warp == 1) umma::tmem_alloc(&bars->tmem_base, 256);
+  if (warp == MMA_WARP) umma::tmem_alloc(&bars->tmem_base, 256);
   umma::fence_proxy_async_smem();
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
-  if (warp == 0) {
-    // =========================== producer: dy rows m0 .. m0+rows ================================
-    uint32_t g = 0, published = 0;
+  if (warp < NPROD) {
+    // =========================== producers: dy rows m0 .. m0+rows (slab g -> warp g % NPROD) ===
+    uint32_t g = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
       const int m0 = hs * DG_MROWS;
@@ -309,39 +347,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(co
       const int i0 = wt * TILE_M;
       const __nv_bfloat16* img = dy + (size_t)b * Ho * Wo * C;
       for (int s = 0; s <= rows; ++s, ++g) {
+        if ((g % NPROD) != (uint32_t)warp) continue;
         const uint32_t slot = g % RING;
         umma::mbar_wait(&bars->empty[slot], ((g / RING) & 1) ^ 1);
         const int r = m0 + s;
         const bool row_ok = r < Ho;
-        const uint32_t dst0 = umma::smem_u32(s_slab + slot * SLAB);
-        const __nv_bfloat16* rowp = img + (size_t)(row_ok ? r : 0) * Wo * C;
-        for (int c = lane; c < 129 * 4; c += 32) {
-          const int li = c >> 2, cg = c & 3;
-          const int col = i0 + li;
-          const bool ok = row_ok && col < Wo;
-          umma::cp_async16(dst0 + cg * PS + li * 16, rowp + (size_t)(ok ? col : 0) * C + cg * 8, ok ? 16u : 0u);
-        }
-        umma::cp_async_commit();
-        if (g + 1 - published >= INFLIGHT) {
-          umma::cp_async_wait<INFLIGHT - 1>();
-          umma::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) umma::mbar_arrive(&bars->full[published % RING]);
-          ++published;
-        }
+        load_slab<129, 0, PS, 32>(umma::smem_u32(s_slab + slot * SLAB), img + (size_t)(row_ok ? r : 0) * Wo * C, row_ok,
+                                  i0, Wo, lane);
+        umma::cp_async_mbar_arrive_noinc(&bars->full[slot]);
       }
     }
-    umma::cp_async_wait<0>();
-    umma::fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0)
-      for (; published < g; ++published) umma::mbar_arrive(&bars->full[published % RING]);
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // =========================== MMA issuer ==================================================
+  } else if (warp == MMA_WARP) {
+    {
+      // =========================== MMA issuer (whole warp, elected lane issues) =================
       constexpr uint32_t idesc = umma::make_idesc_bf16(TILE_M, C, false, false);
-      const uint32_t wbase = umma::smem_u32(s_w);
-      const uint32_t sbase = umma::smem_u32(s_slab);
+      const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), PS);
+      const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), 512);
+      constexpr uint32_t ab_hi = umma::desc_hi(128);
       // {accumulator (0: row 2m even, 1: row 2m odd, 2: row 2m+1 even, 3: row 2m+1 odd), kh, kw, slab (0: m, 1: m+1), shift}
       constexpr int T[9][5] = {{0, 1, 1, 0, 0}, {1, 1, 0, 0, 1}, {1, 1, 2, 0, 0}, {2, 0, 1, 1, 0}, {2, 2, 1, 0, 0},
                                {3, 0, 0, 1, 1}, {3, 0, 2, 1, 0}, {3, 2, 0, 0, 1}, {3, 2, 2, 0, 0}};
@@ -352,25 +374,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(co
         for (int j = 0; j < rows; ++j, ++mctr) {
           const uint32_t need = g0 + j + 2;
           for (; waited < need; ++waited) umma::mbar_wait(&bars->full[waited % RING], (waited / RING) & 1);
+          umma::fence_proxy_async_smem();
           const uint32_t set = mctr & 1;
           umma::mbar_wait(&bars->acc_empty[set], ((mctr >> 1) & 1) ^ 1);
           umma::tc_fence_after_sync();
-          uint32_t used = 0;      // bit a set once accumulator a has been written for this m
+          const uint32_t slab_lo[2] = {a_lo0 + ((g0 + j) % RING) * (SLAB >> 4), a_lo0 + ((g0 + j + 1) % RING) * (SLAB >> 4)};
+          const uint32_t d0 = tmem + set * 128;
+          if (umma::elect_one())
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int a = T[t][0], tap = T[t][1] * 3 + T[t][2];
-            const uint32_t slab = sbase + ((g0 + j + T[t][3]) % RING) * SLAB + T[t][4] * 16;
+            const bool first_of_acc = (t == 0) || (T[t][0] != T[t - (t > 0 ? 1 : 0)][0]);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da = umma::make_desc(slab + (2 * ks) * PS, PS, 128);
-              const uint64_t db = umma::make_desc(wbase + (tap * 4 + 2 * ks) * 512, 512, 128);
-              umma::mma_bf16(tmem + set * 128 + a * 32, da, db, idesc, (used >> a) & 1u);
-              used |= 1u << a;
-            }
+            for (int ks = 0; ks < 2; ++ks)
+              umma::mma_bf16_lohi(d0 + a * 32, slab_lo[T[t][3]] + T[t][4] + ((2 * ks) * PS >> 4), ab_hi,
+                                  b_lo0 + ((tap * 4 + 2 * ks) * 512 >> 4), ab_hi, idesc,
+                                  (first_of_acc && ks == 0) ? 0u : 1u);
           }
-          umma::mma_commit(&bars->acc_full[set]);
-          umma::mma_commit(&bars->empty[(g0 + j) % RING]);
-          if (j == rows - 1) umma::mma_commit(&bars->empty[(g0 + j + 1) % RING]);
+          if (umma::elect_one()) {
+            umma::mma_commit(&bars->acc_full[set]);
+            umma::mma_commit(&bars->empty[(g0 + j) % RING]);
+            if (j == rows - 1) umma::mma_commit(&bars->empty[(g0 + j + 1) % RING]);
+          }
+          __syncwarp();
         }
         g0 += rows + 1;
       }
@@ -386,9 +412,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(co
       const int i = wt * TILE_M + quarter * 32 + lane;
       for (int j = 0; j < rows; ++j, ++mctr) {
         const uint32_t set = mctr & 1;
-        umma::mbar_wait(&bars->acc_full[set], (mctr >> 1) & 1);
+        uint4 mk[4][4];
+        if (mask != nullptr) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int h = 2 * (m0 + j) + (a >> 1), w = 2 * i + (a & 1);
+            const size_t moff = (((size_t)b * H + (h < H ? h : 0)) * W + (w < W ? w : 0)) * C;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) mk[a][gq] = __ldg(reinterpret_cast<const uint4*>(mask + moff) + gq);
+          }
+        }
+        mbar_wait_relaxed(&bars->acc_full[set], (mctr >> 1) & 1);
         umma::tc_fence_after_sync();
-#pragma unroll 1
+#pragma unroll
         for (int a = 0; a < 4; ++a) {
           uint32_t r[32];
           umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + set * 128 + a * 32, r);
@@ -407,10 +443,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(co
             if (mask) {
 #pragma unroll
               for (int gq = 0; gq < 4; ++gq) {
-                float mk[8];
-                dd::ld8<__nv_bfloat16>(mask + off + gq * 8, mk);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&mk[a][gq]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[gq * 8 + k] = mk[k] > 0.f ? v[gq * 8 + k] : 0.f;
+                for (int k = 0; k < 4; ++k) {
+                  const float2 m = __bfloat1622float2(h2[k]);
+                  v[gq * 8 + 2 * k] = m.x > 0.f ? v[gq * 8 + 2 * k] : 0.f;
+                  v[gq * 8 + 2 * k + 1] = m.y > 0.f ? v[gq * 8 + 2 * k + 1] : 0.f;
+                }
               }
             }
 #pragma unroll
@@ -427,7 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(co
   }
   umma::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem, 256);
+  if (warp == MMA_WARP) umma::tmem_dealloc(tmem, 256);
 }
 
 // ================================================================================================
@@ -439,8 +478,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(co
 // blocks are useful.  kw is again a 16-byte shift of the A start address, one 64-column TMEM
 // accumulator per kw, accumulated over every work item of the CTA and written out ONCE at the end
 // as [cta][q][tap][ci][co] partials that an ordered reduction kernel folds (deterministic).
-// Stage = 4 dy rows + 6 x rows of a 128-pixel column strip, double buffered; warps 0,1,3 are
-// cp.async producers, warp 2 issues the MMAs, all four warps run the final epilogue.
+// Stage = 4 dy rows + 6 x rows of a 128-pixel column strip, double buffered; warps 0..3 are
+// cp.async producers and run the final epilogue, warp 4 issues the MMAs.
 // ================================================================================================
 // Stride 2 (c3): one dy row per stage, x rows 2ho-1..2ho+1 (+ one junk row that only feeds the unused
 // D block r = 3) in [parity][row][cg] planes so that the (row, cg) chunks keep one uniform stride;
@@ -466,8 +505,9 @@ struct WgBars {
   uint32_t tmem_base;
 };
 
+constexpr int WG_THREADS = 160;
 template <int STRIDE>
-__global__ void __launch_bounds__(128, 1) conv3x3_c32_wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x,
                                                                        const __nv_bfloat16* __restrict__ dy,
                                                                        float* __restrict__ partial, int B, int H,
                                                                        int W, int Ho, int Wo) {
@@ -476,25 +516,25 @@ __global__ void __launch_bounds__(128, 1) conv3x3_c32_wgrad_tc_kernel(const __nv
   constexpr int WG_PARTIAL = G::PARTIAL;
   extern __shared__ __align__(1024) uint8_t smem[];
   WgBars* bars = reinterpret_cast<WgBars*>(smem + 2 * WG_STAGE_BYTES);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role code stays on the uniform datapath
   const int wtiles = (Wo + TILE_M - 1) / TILE_M;
   const int hsegs = (Ho + WG_ROWS - 1) / WG_ROWS;
   const int items = B * wtiles * hsegs;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->full[i], 3); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->full[i], 128); umma::mbar_init(&bars->empty[i], 1); }
     umma::mbar_init(&bars->done, 1);
     umma::fence_mbar_init();
   }
-  if (warp == 2) umma::tmem_alloc(&bars->tmem_base, 256);
+  if (warp == 4) umma::tmem_alloc(&bars->tmem_base, 256);
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
-  if (warp != 2) {
-    // =========================== producers (warps 0, 1, 3) =====================================
-    const int pl = (warp == 3 ? 2 : warp) * 32 + lane;      // 0..95
+  if (warp < 4) {
+    // =========================== producers (warps 0..3) ========================================
     uint32_t n = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
@@ -505,43 +545,35 @@ __global__ void __launch_bounds__(128, 1) conv3x3_c32_wgrad_tc_kernel(const __nv
       const uint32_t ds = xs + WG_X_BYTES;
       const __nv_bfloat16* ximg = x + (size_t)b * H * W * C;
       const __nv_bfloat16* dimg = dy + (size_t)b * Ho * Wo * C;
-      constexpr int XCH = WG_XROWS * G::XPIX * 4;
-      for (int c = pl; c < XCH; c += 96) {
-        const int cg = c & 3, t = c >> 2;
-        const int r = t / G::XPIX, li = t - r * G::XPIX;
-        const int row = h0 * STRIDE - 1 + r, col = w0 * STRIDE - 1 + li;
-        const bool ok = row >= 0 && row < H && col >= 0 && col < W;
-        uint32_t dst;
-        if (STRIDE == 1) dst = xs + (r * 4 + cg) * PS + li * 16;
-        else dst = xs + ((li & 1) * (G::XROWS_ALLOC * 4) + r * 4 + cg) * PS + (li >> 1) * 16;
-        umma::cp_async16(dst, ximg + ((size_t)(ok ? row : 0) * W + (ok ? col : 0)) * C + cg * 8, ok ? 16u : 0u);
+#pragma unroll
+      for (int r = 0; r < WG_XROWS; ++r) {
+        const int row = h0 * STRIDE - 1 + r;
+        const bool row_ok = row >= 0 && row < H;
+        load_slab<G::XPIX, STRIDE == 2 ? G::XROWS_ALLOC * 4 : 0>(xs + (r * 4) * PS, ximg + (size_t)(row_ok ? row : 0) * W * C,
+                                                                 row_ok, w0 * STRIDE - 1, W, tid);
       }
-      constexpr int DCH = WG_ROWS * TILE_M * 4;
-      for (int c = pl; c < DCH; c += 96) {
-        const int cg = c & 3, t = c >> 2;
-        const int r = t >> 7, li = t & 127;
-        const int row = h0 + r, col = w0 + li;
-        const bool ok = row < Ho && col < Wo;
-        umma::cp_async16(ds + (r * 4 + cg) * PSD + li * 16,
-                         dimg + ((size_t)(ok ? row : 0) * Wo + (ok ? col : 0)) * C + cg * 8, ok ? 16u : 0u);
+#pragma unroll
+      for (int r = 0; r < WG_ROWS; ++r) {
+        const int row = h0 + r;
+        const bool row_ok = row < Ho;
+        load_slab<TILE_M, 0, PSD>(ds + (r * 4) * PSD, dimg + (size_t)(row_ok ? row : 0) * Wo * C, row_ok, w0, Wo, tid);
       }
-      umma::cp_async_commit();
-      umma::cp_async_wait<0>();
-      umma::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&bars->full[stage]);
+      umma::cp_async_mbar_arrive_noinc(&bars->full[stage]);     // published when this thread's copies land
     }
-  } else if (lane == 0) {
-    // =========================== MMA issuer ====================================================
+  } else {
+    // =========================== MMA issuer (warp 4: whole warp loops, elected lane issues) =====
     constexpr uint32_t idesc = umma::make_idesc_bf16(128, G::N, true, true);
     uint32_t n = 0;
     uint32_t fresh = 1;     // accumulators not yet written
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       const uint32_t stage = n & 1;
       umma::mbar_wait(&bars->full[stage], (n >> 1) & 1);
+      umma::fence_proxy_async_smem();
       umma::tc_fence_after_sync();
       const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
-      const uint32_t ds = xs + WG_X_BYTES;
+      const uint32_t x_lo = umma::desc_lo(xs, 128), d_lo = umma::desc_lo(xs + WG_X_BYTES, 128);
+      constexpr uint32_t x_hi = umma::desc_hi(PS), d_hi = umma::desc_hi(PSD);
+      if (umma::elect_one())
 #pragma unroll
       for (int p = 0; p < (STRIDE == 1 ? WG_ROWS / 2 : 1); ++p) {
 #pragma unroll
@@ -550,23 +582,23 @@ __global__ void __launch_bounds__(128, 1) conv3x3_c32_wgrad_tc_kernel(const __nv
           const uint32_t a_off = STRIDE == 1 ? (2 * p * 4) * PS + kw * 16
                                              : (kw == 1 ? G::XROWS_ALLOC * 4 * PS : 0) + (kw == 2 ? 16 : 0);
 #pragma unroll
-          for (int ks = 0; ks < TILE_M / 16; ++ks) {
-            const uint64_t da = umma::make_desc(xs + a_off + ks * 256, 128, PS);
-            const uint64_t db = umma::make_desc(ds + (2 * p * 4) * PSD + ks * 256, 128, PSD);
-            umma::mma_bf16(tmem + kw * 64, da, db, idesc, (fresh && p == 0 && ks == 0) ? 0u : 1u);
-          }
+          for (int ks = 0; ks < TILE_M / 16; ++ks)
+            umma::mma_bf16_lohi(tmem + kw * 64, x_lo + ((a_off + ks * 256) >> 4), x_hi,
+                                d_lo + (((2 * p * 4) * PSD + ks * 256) >> 4), d_hi, idesc,
+                                (fresh && p == 0 && ks == 0) ? 0u : 1u);
         }
       }
       fresh = 0;
-      umma::mma_commit(&bars->empty[stage]);
+      if (umma::elect_one()) umma::mma_commit(&bars->empty[stage]);
+      __syncwarp();
     }
-    umma::mma_commit(&bars->done);
+    if (umma::elect_one()) umma::mma_commit(&bars->done);
   }
-  // =========================== epilogue: TMEM -> per-CTA partials ================================
+  // =========================== epilogue: TMEM -> per-CTA partials (warps 0..3) ===================
   __syncwarp();
-  umma::mbar_wait(&bars->done, 0);
-  umma::tc_fence_after_sync();
-  {
+  if (warp < 4) {
+    mbar_wait_relaxed(&bars->done, 0);
+    umma::tc_fence_after_sync();
     const int r = warp;                      // TMEM lane quarter = x row offset r; lane = ci
     float* out = partial + (size_t)blockIdx.x * WG_PARTIAL;
 #pragma unroll 1
@@ -589,7 +621,7 @@ __global__ void __launch_bounds__(128, 1) conv3x3_c32_wgrad_tc_kernel(const __nv
   }
   umma::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) umma::tmem_dealloc(tmem, 256);
+  if (warp == 4) umma::tmem_dealloc(tmem, 256);
 }
 
 // per-channel sums of an NHWC bf16 tensor (bias gradient): partial[blk][32]
@@ -632,6 +664,368 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int ns
 }
 
 constexpr int kDbBlocks = dd::kSMs * 4;
+
+
+// ================================================================================================
+// First encoder conv (3 -> 32, components.py:19,41) on the tensor cores, stitch folded in.
+// The fp32 input (six views or a mosaic, NCHW) is converted by the producer warps into ONE plane
+// per input row: [pixel][8 ch] bf16 = 16 B per pixel with channels 0..2 = image, 3 = 1.0 (used by
+// the weight-gradient kernel for the bias gradient), 4..7 = 0.  With K = 8 real channels per tap a
+// K = 16 MMA covers TWO horizontally adjacent taps by giving the A descriptor LBO = 16 B (the second
+// K chunk is the same plane one pixel further on): 6 MMAs (M=128, N=32) per output row.
+// ================================================================================================
+constexpr int C1_NPROD = 6;
+constexpr int C1_MMA_WARP = C1_NPROD;
+constexpr int C1_THREADS = 32 * (C1_NPROD + 1 + 4);
+constexpr int C1_RING = 12;
+constexpr int C1_WBYTES = 6 * 1024;                 // [kh][pair][kchunk][co][8 ch] bf16
+constexpr int C1_SMEM = C1_WBYTES + C1_RING * PS + 1024;
+
+struct C1Bars {
+  uint64_t full[C1_RING], empty[C1_RING], acc_full[NACC], acc_empty[NACC];
+  uint32_t tmem_base;
+};
+
+// pointer to channel 0 of (b, mosaic row h, mosaic column wm); channel stride returned in cstride
+template <bool IS_VIEWS>
+__device__ __forceinline__ const float* c1_src(const float* __restrict__ in, int b, int h, int wm, int H, int Wm,
+                                               size_t& cstride) {
+  if (IS_VIEWS) {
+    const int W = Wm / 6;
+    const int j = wm / W, w = wm - j * W;
+    cstride = (size_t)H * W;
+    return in + (((size_t)b * 6 + dd::view_of_slot(j)) * 3) * cstride + (size_t)h * W + w;
+  }
+  cstride = (size_t)H * Wm;
+  return in + ((size_t)b * 3) * cstride + (size_t)h * Wm + wm;
+}
+
+// one input row -> [pixel][8 ch] bf16 plane (130 pixels), by one warp
+template <bool IS_VIEWS>
+__device__ __forceinline__ void c1_load_row(uint8_t* __restrict__ slab, const float* __restrict__ in, int b, int r, int c0,
+                                            int H, int Wm, int lane) {
+  float v[5][3];
+  bool ok[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int li = lane + 32 * k, col = c0 + li;
+    ok[k] = li < 130 && r >= 0 && r < H && col >= 0 && col < Wm;
+    if (ok[k]) {
+      size_t cs;
+      const float* p = c1_src<IS_VIEWS>(in, b, r, col, H, Wm, cs);
+      v[k][0] = __ldg(p); v[k][1] = __ldg(p + cs); v[k][2] = __ldg(p + 2 * cs);
+    } else {
+      v[k][0] = v[k][1] = v[k][2] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int li = lane + 32 * k;
+    if (li < 130) {
+      uint4 q;
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[k][0], v[k][1]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(v[k][2], ok[k] ? 1.0f : 0.0f);
+      q.x = *reinterpret_cast<uint32_t*>(&a); q.y = *reinterpret_cast<uint32_t*>(&c); q.z = 0u; q.w = 0u;
+      *reinterpret_cast<uint4*>(slab + li * 16) = q;
+    }
+  }
+}
+
+template <bool IS_VIEWS>
+__global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const float* __restrict__ in,
+                                                                    const float* __restrict__ w_oihw,
+                                                                    const float* __restrict__ bias,
+                                                                    __nv_bfloat16* __restrict__ out, int B, int H, int Wm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_slab = smem + C1_WBYTES;
+  C1Bars* bars = reinterpret_cast<C1Bars*>(smem + C1_WBYTES + C1_RING * PS);
+  __shared__ float s_bias[C];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wtiles = (Wm + TILE_M - 1) / TILE_M;
+  const int hsegs = (H + ROWS - 1) / ROWS;
+  const int items = B * wtiles * hsegs;
+
+  // weights: B operand of (kh, pair p): K chunk kc holds tap kw = 2p + kc, channels 0..7 (3 real)
+  for (int i = tid; i < C1_WBYTES / 2; i += C1_THREADS) {
+    const int ch = i & 7, co = (i >> 3) & 31, kc = (i >> 8) & 1, p = (i >> 9) & 1, kh = i >> 10;
+    const int kw = 2 * p + kc;
+    const float v = (kw < 3 && ch < 3) ? w_oihw[((co * 3 + ch) * 3 + kh) * 3 + kw] : 0.f;
+    reinterpret_cast<__nv_bfloat16*>(s_w)[i] = __float2bfloat16_rn(v);
+  }
+  for (int i = tid; i < C1_RING * PS / 16; i += C1_THREADS) reinterpret_cast<uint4*>(s_slab)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < C) s_bias[tid] = bias[tid];
+  if (tid == 0) {
+    for (int i = 0; i < C1_RING; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 4); }
+    umma::fence_mbar_init();
+  }
+  if (warp == C1_MMA_WARP) umma::tmem_alloc(&bars->tmem_base, NACC * 32);
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
+
+  if (warp < C1_NPROD) {
+    // =========================== producers: slab g -> warp g % C1_NPROD =========================
+    uint32_t g = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int h0 = hs * ROWS;
+      const int rows = min(ROWS, H - h0);
+      for (int sidx = 0; sidx < rows + 2; ++sidx, ++g) {
+        if ((g % C1_NPROD) != (uint32_t)warp) continue;
+        const uint32_t slot = g % C1_RING;
+        umma::mbar_wait(&bars->empty[slot], ((g / C1_RING) & 1) ^ 1);
+        c1_load_row<IS_VIEWS>(s_slab + slot * PS, in, b, h0 - 1 + sidx, wt * TILE_M - 1, H, Wm, lane);
+        umma::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bars->full[slot]);
+      }
+    }
+  } else if (warp == C1_MMA_WARP) {
+    // =========================== MMA issuer (whole warp, elected lane issues) ===================
+    constexpr uint32_t idesc = umma::make_idesc_bf16(TILE_M, C, false, false);
+    const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), 16);       // second K chunk = next pixel
+    const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), 512);
+    constexpr uint32_t ab_hi = umma::desc_hi(128);
+    uint32_t g0 = 0, waited = 0, row_ctr = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int hs = (it / wtiles) % hsegs;
+      const int rows = min(ROWS, H - hs * ROWS);
+      for (int j = 0; j < rows; ++j, ++row_ctr) {
+        const uint32_t need = g0 + j + 3;
+        for (; waited < need; ++waited) umma::mbar_wait(&bars->full[waited % C1_RING], (waited / C1_RING) & 1);
+        const uint32_t buf = row_ctr % NACC;
+        umma::mbar_wait(&bars->acc_empty[buf], ((row_ctr / NACC) & 1) ^ 1);
+        umma::tc_fence_after_sync();
+        if (umma::elect_one()) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t slab_lo = a_lo0 + ((g0 + j + kh) % C1_RING) * (PS >> 4);
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+              umma::mma_bf16_lohi(tmem + buf * 32, slab_lo + 2 * p, ab_hi, b_lo0 + ((kh * 2 + p) * 1024 >> 4), ab_hi, idesc,
+                                  (kh | p) ? 1u : 0u);
+          }
+          umma::mma_commit(&bars->acc_full[buf]);
+          const int nrel = (j == rows - 1) ? 3 : 1;
+          for (int q = 0; q < nrel; ++q) umma::mma_commit(&bars->empty[(g0 + j + q) % C1_RING]);
+        }
+        __syncwarp();
+      }
+      g0 += rows + 2;
+    }
+  } else {
+    // =========================== epilogue: bias + ReLU -> bf16 NHWC ==============================
+    const int quarter = warp & 3;
+    uint32_t row_ctr = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int h0 = hs * ROWS;
+      const int rows = min(ROWS, H - h0);
+      const int wo = wt * TILE_M + quarter * 32 + lane;
+      for (int j = 0; j < rows; ++j, ++row_ctr) {
+        const uint32_t buf = row_ctr % NACC;
+        mbar_wait_relaxed(&bars->acc_full[buf], (row_ctr / NACC) & 1);
+        umma::tc_fence_after_sync();
+        uint32_t r[32];
+        umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * 32, r);
+        umma::tmem_ld_wait();
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bars->acc_empty[buf]);
+        if (wo < Wm) {
+          __nv_bfloat16* dst = out + (((size_t)b * H + h0 + j) * Wm + wo) * C;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            float t8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t8[k] = fmaxf(__uint_as_float(r[gq * 8 + k]) + s_bias[gq * 8 + k], 0.f);
+            dd::st8<__nv_bfloat16>(dst + gq * 8, t8);
+          }
+        }
+      }
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == C1_MMA_WARP) umma::tmem_dealloc(tmem, NACC * 32);
+}
+
+
+// ================================================================================================
+// Weight gradient of the first conv (3 -> 32) on the tensor cores, stitch folded in.
+//   dW[co][c][kh][kw] = sum_{b,h,w} in[b,c,h+kh-1,w+kw-1] * dy[b,h,w,co],   db[co] = sum dy[b,h,w,co]
+// The contraction runs over pixels (both operands MN-major, K = 16 pixels per tcgen05.mma).  The
+// producers convert the fp32 input into "tap-packed" planes: per x row two 8-channel chunks per
+// pixel p, channel j = kw*3 + c (j < 9) = in[c][p + kw - 1], j = 9 = 1.0 (-> bias gradient), rest 0,
+// so the three horizontal taps ride in the M dimension instead of costing three MMAs.
+// Work item = 128-pixel strip x 6 dy rows: A = 8 x rows x 16 channels (M = 128), B = 6 dy rows x 32 co
+// (N = 192); block (r, q) of D is tap kh = r - q, every x row is used (18 of the 48 blocks are
+// taps, the rest is ignored).  One TMEM accumulator per CTA over all its items, written once.
+// ================================================================================================
+constexpr int CW_RB = 6, CW_XR = 8;
+constexpr int CW_X_BYTES = CW_XR * 2 * PSD;            // [x row][half][128 px][8 ch]
+constexpr int CW_DY_BYTES = CW_RB * 4 * PSD;           // [dy row][cg][128 px][8 co]
+constexpr int CW_STAGE = CW_X_BYTES + CW_DY_BYTES;     // 80 KB
+constexpr int CW_SMEM = 2 * CW_STAGE + 1024;
+constexpr int CW_PARTIAL = CW_RB * 3 * 10 * C;         // floats per CTA: [q][kh][j][co]
+
+template <bool IS_VIEWS>
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_c1_wgrad_tc_kernel(const float* __restrict__ in,
+                                                                          const __nv_bfloat16* __restrict__ dy,
+                                                                          float* __restrict__ partial, int B, int H,
+                                                                          int Wm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WgBars* bars = reinterpret_cast<WgBars*>(smem + 2 * CW_STAGE);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wtiles = (Wm + TILE_M - 1) / TILE_M;
+  const int hsegs = (H + CW_RB - 1) / CW_RB;
+  const int items = B * wtiles * hsegs;
+
+  if (tid == 0) {
+    // per stage: 128 plain arrivals (x planes written, fenced) + 128 cp.async arrivals (dy landed)
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->full[i], 256); umma::mbar_init(&bars->empty[i], 1); }
+    umma::mbar_init(&bars->done, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 4) umma::tmem_alloc(&bars->tmem_base, 256);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
+
+  if (warp < 4) {
+    // =========================== producers: thread = pixel of the strip ==========================
+    const int Wv = IS_VIEWS ? Wm / 6 : Wm;
+    const size_t cstride = (size_t)H * Wv;
+    uint32_t n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int h0 = hs * CW_RB, w0 = wt * TILE_M;
+      const uint32_t stage = n & 1;
+      umma::mbar_wait(&bars->empty[stage], ((n >> 1) & 1) ^ 1);
+      uint8_t* xs = smem + stage * CW_STAGE;
+      const uint32_t ds = umma::smem_u32(xs) + CW_X_BYTES;
+      const __nv_bfloat16* dimg = dy + (size_t)b * H * Wm * C;
+#pragma unroll
+      for (int q = 0; q < CW_RB; ++q) {
+        const int row = h0 + q;
+        const bool row_ok = row < H;
+        load_slab<TILE_M, 0, PSD>(ds + (q * 4) * PSD, dimg + (size_t)(row_ok ? row : 0) * Wm * C, row_ok, w0, Wm, tid);
+      }
+      umma::cp_async_mbar_arrive_noinc(&bars->full[stage]);
+      // columns w0+tid-1 .. w0+tid+1: offset of channel 0, row 0 (views: through the mosaic slot map)
+      size_t off[3];
+      bool cok[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int col = w0 + tid + d - 1;
+        cok[d] = col >= 0 && col < Wm;
+        const int cc = cok[d] ? col : 0;
+        if (IS_VIEWS) {
+          const int j = cc / Wv, w = cc - j * Wv;
+          off[d] = (((size_t)b * 6 + dd::view_of_slot(j)) * 3) * cstride + w;
+        } else {
+          off[d] = ((size_t)b * 3) * cstride + cc;
+        }
+      }
+#pragma unroll 2
+      for (int r = 0; r < CW_XR; ++r) {
+        const int row = h0 - 1 + r;
+        const bool row_ok = row >= 0 && row < H;
+        float v[3][3];                       // [kw][c]
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            v[d][c] = (row_ok && cok[d]) ? __ldg(in + off[d] + c * cstride + (size_t)row * Wv) : 0.f;
+        uint4 lo, hi;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(v[0][0], v[0][1]); lo.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[0][2], v[1][0]); lo.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[1][1], v[1][2]); lo.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[2][0], v[2][1]); lo.w = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[2][2], 1.0f);    hi.x = *reinterpret_cast<uint32_t*>(&t);
+        hi.y = hi.z = hi.w = 0u;
+        *reinterpret_cast<uint4*>(xs + (r * 2) * PSD + tid * 16) = lo;
+        *reinterpret_cast<uint4*>(xs + (r * 2 + 1) * PSD + tid * 16) = hi;
+      }
+      umma::fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core's reads
+      umma::mbar_arrive(&bars->full[stage]);
+    }
+  } else {
+    // =========================== MMA issuer (warp 4) ===============================================
+    constexpr uint32_t idesc = umma::make_idesc_bf16(128, CW_RB * 32, true, true);
+    constexpr uint32_t ab_hi = umma::desc_hi(PSD);       // SBO: stride between 8-channel chunks (planes)
+    uint32_t n = 0, fresh = 1;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const uint32_t stage = n & 1;
+      umma::mbar_wait(&bars->full[stage], (n >> 1) & 1);
+      umma::fence_proxy_async_smem();
+      umma::tc_fence_after_sync();
+      const uint32_t xs = umma::smem_u32(smem + stage * CW_STAGE);
+      const uint32_t x_lo = umma::desc_lo(xs, 128), d_lo = umma::desc_lo(xs + CW_X_BYTES, 128);
+      if (umma::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < TILE_M / 16; ++ks)
+          umma::mma_bf16_lohi(tmem, x_lo + ks * 16, ab_hi, d_lo + ks * 16, ab_hi, idesc, (fresh && ks == 0) ? 0u : 1u);
+        umma::mma_commit(&bars->empty[stage]);
+      }
+      fresh = 0;
+      __syncwarp();
+    }
+    if (umma::elect_one()) umma::mma_commit(&bars->done);
+  }
+  // =========================== epilogue: TMEM -> per-CTA partials (warps 0..3) ======================
+  __syncwarp();
+  if (warp < 4) {
+    mbar_wait_relaxed(&bars->done, 0);
+    umma::tc_fence_after_sync();
+    const int r = 2 * warp + (lane >> 4), j = lane & 15;     // TMEM lane = r*16 + j
+    float* out = partial + (size_t)blockIdx.x * CW_PARTIAL;
+#pragma unroll 1
+    for (int q = 0; q < CW_RB; ++q) {
+      uint32_t v[32];
+      umma::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + q * 32, v);
+      umma::tmem_ld_wait();
+      const int kh = r - q;
+      if (kh >= 0 && kh <= 2 && j < 10) {
+        float4* dst = reinterpret_cast<float4*>(out + ((q * 3 + kh) * 10 + j) * C);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4)
+          dst[g4] = make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]),
+                                __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
+      }
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) umma::tmem_dealloc(tmem, 256);
+}
+
+// block (kh, j): sums partial[cta][q][kh][j][co] over the nslots = CTAs x 6 (cta, q) slots in a fixed order
+__global__ void __launch_bounds__(256) c1_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nslots,
+                                                                 float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[8][C];
+  const int kh = blockIdx.x / 10, j = blockIdx.x % 10;
+  const int co = threadIdx.x & 31, g = threadIdx.x >> 5;
+  float s = 0.f;
+  for (int slot = g; slot < nslots; slot += 8) s += partial[(((size_t)slot * 3 + kh) * 10 + j) * C + co];
+  red[g][co] = s;
+  __syncthreads();
+  if (g == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][co];
+    if (j < 9) dw[((co * 3 + j % 3) * 3 + kh) * 3 + j / 3] = t;
+    else if (kh == 1) db[co] = t;
+  }
+}
 
 }  // namespace
 
@@ -676,7 +1070,7 @@ static int wgrad_tc_launch(const void* x, const void* dy, float* dw, float* db, 
   auto k = conv3x3_c32_wgrad_tc_kernel<STRIDE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
   if (e != cudaSuccess) return fail((int)e, "wgrad_tc: cudaFuncSetAttribute(%d): %s", G::SMEM, cudaGetErrorString(e));
-  k<<<grid, 128, G::SMEM, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, B, H, W, Ho, Wo);
+  k<<<grid, WG_THREADS, G::SMEM, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, B, H, W, Ho, Wo);
   if (int err = check_launch("conv3x3_c32_wgrad_tc")) return err;
   const long long npix = (long long)B * Ho * Wo;
   const int dbg = (int)((npix + 63) / 64 < kDbBlocks ? (npix + 63) / 64 : kDbBlocks);
@@ -684,6 +1078,36 @@ static int wgrad_tc_launch(const void* x, const void* dy, float* dw, float* db, 
   if (int err = check_launch("colsum_nhwc_bf16")) return err;
   wgrad_tc_reduce_kernel<<<(9 * C * C + C + 255) / 256, 256, 0, st>>>(partial, grid * G::NQ, dbp, dbg, dw, db);
   return check_launch("wgrad_tc_reduce");
+}
+
+int conv_c1_fwd_tc(const float* in, int in_is_views, const float* w, const float* bias, void* out, int B, int H, int Wm,
+                   cudaStream_t st) {
+  const int items = B * ((Wm + TILE_M - 1) / TILE_M) * ((H + ROWS - 1) / ROWS);
+  const int grid = items < kSMs ? items : kSMs;
+  auto launch1 = [&](auto k) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "conv_c1_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    k<<<grid, C1_THREADS, C1_SMEM, st>>>(in, w, bias, (__nv_bfloat16*)out, B, H, Wm);
+    return check_launch("conv_c1_tc");
+  };
+  return in_is_views ? launch1(conv_c1_tc_kernel<true>) : launch1(conv_c1_tc_kernel<false>);
+}
+
+int conv_c1_wgrad_tc(const float* in, int in_is_views, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes,
+                     int B, int H, int Wm, cudaStream_t st) {
+  const int items = B * ((Wm + TILE_M - 1) / TILE_M) * ((H + CW_RB - 1) / CW_RB);
+  const int grid = items < kSMs ? items : kSMs;
+  const size_t need = (size_t)grid * CW_PARTIAL * sizeof(float);
+  if (ws_bytes < need) return fail(DD_ERR_WORKSPACE, "tcgen05 c1 wgrad: workspace %zu < %zu", ws_bytes, need);
+  auto launch1 = [&](auto k) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "conv_c1_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    k<<<grid, WG_THREADS, CW_SMEM, st>>>(in, (const __nv_bfloat16*)dy, (float*)ws, B, H, Wm);
+    return check_launch("conv_c1_wgrad_tc");
+  };
+  if (int err = in_is_views ? launch1(conv_c1_wgrad_tc_kernel<true>) : launch1(conv_c1_wgrad_tc_kernel<false>)) return err;
+  c1_wgrad_tc_reduce_kernel<<<30, 256, 0, st>>>((const float*)ws, grid * CW_RB, dw, db);
+  return check_launch("c1_wgrad_tc_reduce");
 }
 
 int conv3x3_c32_wgrad_tc(const void* x, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int B, int H,

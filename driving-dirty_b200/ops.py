@@ -129,7 +129,7 @@ class EncoderConvStack(torch.autograd.Function):
         w1, b1, w2, b2, w3, b3 = (_c(t.detach().float()) for t in (w1, b1, w2, b2, w3, b3))
         a1 = torch.empty(B, H, Wm, 32, dtype=act_dtype, device=dev)
         call("dd_conv_c1_fwd", inp.data_ptr(), int(is_views), w1.data_ptr(), b1.data_ptr(), a1.data_ptr(), code,
-             B, H, Wm, st)
+             B, H, Wm, impl, st)
         a2 = torch.empty_like(a1)
         call("dd_conv3x3_c32_fwd", a1.data_ptr(), w2.data_ptr(), b2.data_ptr(), a2.data_ptr(), code, B, H, Wm, 1,
              impl, st)
@@ -177,7 +177,7 @@ class EncoderConvStack(torch.autograd.Function):
         del da2
         dw1, db1 = torch.empty(32, 3, 3, 3, **f32), torch.empty(32, **f32)
         call("dd_conv_c1_wgrad", inp.data_ptr(), int(is_views), da1.data_ptr(), code, dw1.data_ptr(), db1.data_ptr(),
-             ws.data_ptr(), ws_n, B, H, Wm, st)
+             ws.data_ptr(), ws_n, B, H, Wm, impl, st)
         return None, dw1, db1, dw2, db2, dw3, db3, None, None, None
 
 

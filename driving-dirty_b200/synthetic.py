@@ -1,0 +1,41 @@
+"""Synthetic scenes and random-init models for benchmarks and demos: there is no
+dataset or checkpoint in the build image, so throughput is measured on random views / road maps
+and default-initialised weights of the reference's architecture.  Product code: no oracle import."""
+import os
+import tempfile
+from argparse import Namespace
+
+import torch
+
+
+def scene_batch(batch: int, view_h: int = 256, view_w: int = 306, map_hw: int = 800, seed: int = 20200505):
+    """views [B,6,3,H,W] fp32 in [0,1) (ToTensor range) and a bool road map [B,map,map] (CPU tensors)."""
+    g = torch.Generator().manual_seed(seed)
+    views = torch.rand(batch, 6, 3, view_h, view_w, generator=g)
+    road = torch.rand(batch, map_hw, map_hw, generator=g) > 0.5
+    return views, road
+
+
+def random_roadmap_model(hidden=256, latent=128, view_h=256, view_w=306, dtype="bf16", device="cuda:0",
+                         map_size=800, seed=20200505, state_dict=None):
+    """RoadMapBCE with torch-default random weights (or ``state_dict``), built the way the reference
+    demands: through an AE checkpoint on disk (roadmap_bce_v2.py:43)."""
+    from .autoencoder.autoencoder import BasicAE, default_hparams
+    from .lightning_compat import save_checkpoint
+    from .roadmap_model.roadmap_bce_v2 import RoadMapBCE
+
+    torch.manual_seed(seed)
+    hp = default_hparams(hidden_dim=hidden, latent_dim=latent, input_width=6 * view_w, input_height=view_h,
+                         output_width=view_w, output_height=view_h, compute_dtype=dtype)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ae.ckpt")
+        ae = BasicAE(hp)
+        save_checkpoint(ae, path)
+        del ae
+        model = RoadMapBCE(Namespace(pretrained_path=path, learning_rate=1e-3, batch_size=4,
+                                     output_img_freq=10 ** 9, unfreeze_epoch_no=0, link="", compute_dtype=dtype,
+                                     map_size=map_size))
+    if state_dict is not None:
+        res = model.load_state_dict({k: v.clone() for k, v in state_dict.items()}, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+    return model.to(device)

@@ -64,10 +64,10 @@ int dd_stitch_u8(const uint8_t* views, float* mosaic, int B, int H, int W, void*
  * the stitch is folded into the loads, Wm = 6W) or a mosaic / any NCHW image [B,3,H,Wm]
  * (in_is_views=0).  out: NHWC [B,H,Wm,32] of out_dtype. */
 int dd_conv_c1_fwd(const float* in, int in_is_views, const float* w_oihw, const float* bias,
-                   void* out, int out_dtype, int B, int H, int Wm, void* stream);
+                   void* out, int out_dtype, int B, int H, int Wm, int impl, void* stream);
 /* dW [32,3,3,3], db [32] from dy = dL/d(out) ALREADY masked by out>0.  workspace: see below. */
 int dd_conv_c1_wgrad(const float* in, int in_is_views, const void* dy, int dtype, float* dw,
-                     float* db, void* workspace, size_t ws_bytes, int B, int H, int Wm,
+                     float* db, void* workspace, size_t ws_bytes, int B, int H, int Wm, int impl,
                      void* stream);
 
 /* c2 / c3: 32->32, 3x3, pad 1, stride 1 or 2, + bias + ReLU; NHWC in [B,H,W,32] ->

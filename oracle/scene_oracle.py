@@ -95,8 +95,12 @@ def _weight_as(w, dtype):
 def encoder_convs(p: dict, x: torch.Tensor, prefix: str = "ae.encoder.", act_dtype=None, weight_dtype=None):
     """components.py:41-43: relu(c1), relu(c2), relu(c3 stride 2), all 3x3 pad 1.
     ``act_dtype`` / ``weight_dtype`` (default None = the reference's fp32) emulate the storage
-    rounding points of the bf16 path: a1, a2, a3 and their gradients; c2/c3 weights as operands."""
-    a1 = _store(F.relu(F.conv2d(x, p[prefix + "c1.weight"], p[prefix + "c1.bias"], padding=1)), act_dtype)
+    rounding points of the bf16 path: a1, a2, a3 and their gradients; the conv weights and the
+    input image as tensor-core operands."""
+    if weight_dtype is not None and weight_dtype != torch.float32:
+        x = x.to(weight_dtype).float()     # the tensor-core c1 reads the image as bf16 operands too
+    a1 = _store(F.relu(F.conv2d(x, _weight_as(p[prefix + "c1.weight"], weight_dtype), p[prefix + "c1.bias"],
+                                padding=1)), act_dtype)
     a2 = _store(F.relu(F.conv2d(a1, _weight_as(p[prefix + "c2.weight"], weight_dtype), p[prefix + "c2.bias"],
                                 padding=1)), act_dtype)
     a3 = _store(F.relu(F.conv2d(a2, _weight_as(p[prefix + "c3.weight"], weight_dtype), p[prefix + "c3.bias"],

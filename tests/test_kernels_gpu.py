@@ -205,8 +205,11 @@ def test_conv3x3_dgrad_wgrad_simt(dd, dtype, tol, B, H, W, stride):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
-@pytest.mark.parametrize("B,H,W", [(2, 16, 20), (1, 10, 14), (1, 33, 7)])
-def test_conv_c1_fwd_and_wgrad(dd, dtype, tol, B, H, W):
+@pytest.mark.parametrize("B,H,W", [(2, 16, 20), (1, 10, 14), (1, 33, 7), (2, 40, 50)])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_conv_c1_fwd_and_wgrad(dd, dtype, tol, B, H, W, impl):
+    if impl == 2 and dtype == torch.float32:
+        pytest.skip("tcgen05 conv is bf16 only")
     from driving_dirty_b200._lib import call, dtype_code, load, stream_ptr
     views, _ = so.synthetic_scene_batch(B, H, W, map_hw=4, seed=31)
     _, w, b = _conv_inputs(1, 4, 4, seed=32, cin=3)
@@ -219,7 +222,8 @@ def test_conv_c1_fwd_and_wgrad(dd, dtype, tol, B, H, W):
     outs = []
     for is_views, src in ((1, views.cuda()), (0, mosaic.cuda())):
         out = torch.empty(B, H, Wm, 32, dtype=dtype, device="cuda")
-        call("dd_conv_c1_fwd", src.data_ptr(), is_views, wc.data_ptr(), bc.data_ptr(), out.data_ptr(), code, B, H, Wm, st)
+        call("dd_conv_c1_fwd", src.data_ptr(), is_views, wc.data_ptr(), bc.data_ptr(), out.data_ptr(), code, B, H, Wm,
+             impl, st)
         assert rel_max_err(to_nchw(out), y) < tol
         outs.append(out)
     assert torch.equal(outs[0], outs[1])     # folding the stitch changes nothing
@@ -232,7 +236,7 @@ def test_conv_c1_fwd_and_wgrad(dd, dtype, tol, B, H, W):
     for is_views, src in ((1, views.cuda()), (0, mosaic.cuda())):
         dw, db = torch.empty(32, 3, 3, 3, device="cuda"), torch.empty(32, device="cuda")
         call("dd_conv_c1_wgrad", src.data_ptr(), is_views, dyin.data_ptr(), code, dw.data_ptr(), db.data_ptr(),
-             ws.data_ptr(), n, B, H, Wm, st)
+             ws.data_ptr(), n, B, H, Wm, impl, st)
         assert rel_max_err(dw, wq.grad) < tol
         assert rel_max_err(db, bq.grad) < tol
 
