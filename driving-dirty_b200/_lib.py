@@ -46,9 +46,21 @@ SIGNATURES = {
     "dd_bce_bwd": (_I, [_P, _P, _I, _P, _P, _L, _P]),
     "dd_bce_ts_workspace_bytes": (_Z, []),
     "dd_threat_score_f32": (_I, [_P, _P, _P, _P, _Z, _L, _P]),
+    "dd_conv2d_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
+    "dd_conv2d_dgrad": (_I, [_P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "dd_conv2d_wgrad": (_I, [_P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "dd_conv2d_workspace_bytes": (_Z, [_P]),
     "dd_mse_fwd": (_I, [_P, _P, _P, _P, _Z, _L, _P]),
     "dd_mse_bwd": (_I, [_P, _P, _P, _P, _L, _P]),
 }
+
+
+
+class ConvDesc(ctypes.Structure):
+    """dd_conv_desc (include/dd_b200.h): the forward layer, for all three passes."""
+    _fields_ = [(n, c_int) for n in ("B", "Cin", "Cout", "Hi", "Wi", "Ho", "Wo", "kh", "kw", "sh", "sw", "ph", "pw",
+                                     "dh", "dw", "transposed")]
+
 
 _lib = None
 

@@ -44,7 +44,7 @@ class BasicAE(LightningModule):
         return Encoder(hidden_dim, latent_dim, in_channels, input_height, input_width, self.compute_dtype)
 
     def init_decoder(self, hidden_dim, latent_dim, in_channels, output_height, output_width):
-        return Decoder(hidden_dim, latent_dim, in_channels, output_height, output_width)
+        return Decoder(hidden_dim, latent_dim, in_channels, output_height, output_width, self.compute_dtype)
 
     def six_to_one_task(self, x):
         """autoencoder.py:53-73: stitch, draw ``np.random.randint(0, 5)`` (host RNG, one slot per

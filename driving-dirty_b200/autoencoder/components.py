@@ -108,8 +108,9 @@ class Decoder(nn.Module):
     """components.py:55-93: latent -> DenseBlock x2 -> [B,64,h,w] -> 3 ConvTranspose2d+ReLU -> 1x1
     ConvTranspose2d.  Parameters, shapes and init order match the reference."""
 
-    def __init__(self, hidden_dim, latent_dim, in_channels, output_height, output_width):
+    def __init__(self, hidden_dim, latent_dim, in_channels, output_height, output_width, compute_dtype="fp32"):
         super().__init__()
+        self.compute_dtype = resolve_dtype(compute_dtype)
         self.deconv_dim_h, self.deconv_dim_w = self._calculate_output_size(in_channels, output_height, output_width)
         self.latent_dim = latent_dim
         self.fc1 = DenseBlock(latent_dim, hidden_dim)
@@ -134,4 +135,4 @@ class Decoder(nn.Module):
         x = self.fc1(z)
         x = self.fc2(x)
         x = x.view(x.size(0), 64, self.deconv_dim_h, self.deconv_dim_w)
-        return ops.decoder_deconv_stack(x, self.dc1, self.dc2, self.dc3, self.dc4)
+        return ops.decoder_deconv_stack(x, self.dc1, self.dc2, self.dc3, self.dc4, act_dtype=self.compute_dtype)

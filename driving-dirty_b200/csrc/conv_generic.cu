@@ -1,0 +1,397 @@
+// Generic 2-D convolution / transposed convolution on the CUDA cores (fp32 accumulate, fp32 or bf16
+// NHWC storage): any kernel size, stride, padding, dilation, channel counts.  This is the fp32
+// parity path (and the on-device check for tensor-core versions) of every layer of the scene
+// pipeline that is not one of the three encoder convs:
+//   Decoder dc1..dc4            components.py:70-73,89-92   (ConvTranspose2d k3 p1, k3 p1, k2 s2, k1)
+//   SpatialMappingCNN convs     spatial_bb/components.py:18-26,34-76 (1x50 / 52x1 stride (3,2), 3x3 valid)
+//   RoadMapBoxesMergingCNN      spatial_bb/components.py:129-139,149-168 (1x24 s(1,7), k2 s2 deconv,
+//                               k7 s3 d3 p1, k3 d3, four dilated ConvTranspose2d k7, k2 s2 deconv)
+//
+// Both directions are written as GATHERS over the output pixel:
+//   conv : y[ho,wo,co] = sum_{kh,kw,ci} x[ho*sh - ph + kh*dh, wo*sw - pw + kw*dw, ci] * W[co,ci,kh,kw]
+//   convT: y[ho,wo,co] = sum_{kh,kw,ci} x[(ho + ph - kh*dh)/sh, (wo + pw - kw*dw)/sw, ci] * W[ci,co,kh,kw]
+//          (terms whose division is not exact are absent)
+// so the input gradient of a conv is the convT gather over dy with the SAME weight tensor, and vice
+// versa; the weight gradient of either is one "pivot x shifted" pixel contraction.
+#include "dd_common.cuh"
+
+namespace {
+
+struct Geo {
+  int B, Ci, Co;          // channels of the gathered tensor / of the produced tensor
+  int Hi, Wi, Ho, Wo;     // gathered tensor grid / produced tensor grid
+  int kh, kw, sh, sw, ph, pw, dh, dw;
+  int transposed;         // gather form (see above)
+};
+
+// wg[t][a][b] = w[a][b][t] (swap = 0) or w[b][a][t] (swap = 1); A, Bc = sizes of a, b; T taps
+__global__ void wprep_kernel(const float* __restrict__ w, float* __restrict__ wg, int A, int Bc, int T, int swap) {
+  const int n = A * Bc * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = i % Bc, a = (i / Bc) % A, t = i / (A * Bc);
+    wg[i] = swap ? w[((size_t)b * A + a) * T + t] : w[((size_t)a * Bc + b) * T + t];
+  }
+}
+
+__device__ __forceinline__ bool tap_coord(const Geo& g, int o, int k, int s, int p, int d, int n, int& i) {
+  if (!g.transposed) {
+    i = o * s - p + k * d;
+    return i >= 0 && i < n;
+  }
+  const int t = o + p - k * d;
+  if (t < 0) return false;
+  i = t / s;
+  return (i * s == t) && i < n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / input-gradient gather: thread = 1 output pixel x 16 output channels, CTA = 256 threads,
+// weights of one tap staged in shared memory ([ci][CO_T]) and read as broadcast float4s.
+// act: 0 none, 1 ReLU, 2 sigmoid.  mask (optional, same shape as y): y *= (mask > 0).
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_CI = 128;
+
+template <typename T, int CO_T>
+__global__ void __launch_bounds__(256) conv2d_gather_kernel(const T* __restrict__ x, const float* __restrict__ wg,
+                                                            const float* __restrict__ bias, const T* __restrict__ mask,
+                                                            T* __restrict__ y, Geo g, int act) {
+  constexpr int TPP = CO_T / 16;            // threads per pixel
+  constexpr int PIX = 256 / TPP;
+  __shared__ __align__(16) float s_w[MAX_CI * CO_T];
+  const int tid = threadIdx.x;
+  const int sub = tid % TPP;
+  const long long npix = (long long)g.B * g.Ho * g.Wo;
+  const long long pix = (long long)blockIdx.x * PIX + tid / TPP;
+  const bool live = pix < npix;
+  const int co0 = blockIdx.y * CO_T;
+  int wo = 0, ho = 0, b = 0;
+  if (live) {
+    wo = (int)(pix % g.Wo);
+    ho = (int)((pix / g.Wo) % g.Ho);
+    b = (int)(pix / ((long long)g.Wo * g.Ho));
+  }
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  const bool vec = (g.Ci % 8) == 0;
+  const T* img = x + (size_t)b * g.Hi * g.Wi * g.Ci;
+
+  for (int t = 0; t < g.kh * g.kw; ++t) {
+    __syncthreads();
+    for (int i = tid; i < g.Ci * CO_T; i += 256) {
+      const int c = i % CO_T, ci = i / CO_T;
+      s_w[i] = (co0 + c < g.Co) ? __ldg(wg + ((size_t)t * g.Ci + ci) * g.Co + co0 + c) : 0.f;
+    }
+    __syncthreads();
+    int hi, wi;
+    const bool ok = live && tap_coord(g, ho, t / g.kw, g.sh, g.ph, g.dh, g.Hi, hi) &&
+                    tap_coord(g, wo, t % g.kw, g.sw, g.pw, g.dw, g.Wi, wi);
+    if (!ok) continue;
+    const T* px = img + ((size_t)hi * g.Wi + wi) * g.Ci;
+    const float4* w4 = reinterpret_cast<const float4*>(s_w + sub * 16);
+    if (vec) {
+      for (int c8 = 0; c8 < g.Ci; c8 += 8) {
+        float xv[8];
+        dd::ld8<T>(px + c8, xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float4* wr = w4 + (size_t)(c8 + e) * (CO_T / 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 ww = wr[q];
+            acc[4 * q + 0] = fmaf(xv[e], ww.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(xv[e], ww.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(xv[e], ww.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(xv[e], ww.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    } else {
+      for (int ci = 0; ci < g.Ci; ++ci) {
+        const float xv = dd::ld<T>(px + ci);
+        const float4* wr = w4 + (size_t)ci * (CO_T / 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = wr[q];
+          acc[4 * q + 0] = fmaf(xv, ww.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(xv, ww.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xv, ww.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xv, ww.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  if (!live) return;
+  const int cbase = co0 + sub * 16;
+  T* out = y + (size_t)pix * g.Co + cbase;
+  const T* mk = mask ? mask + (size_t)pix * g.Co + cbase : nullptr;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (cbase + k >= g.Co) break;
+    float v = acc[k] + (bias ? __ldg(bias + cbase + k) : 0.f);
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) {
+      const float e = expf(-fabsf(v));
+      const float inv = __frcp_rn(1.0f + e);
+      v = v >= 0.f ? inv : e * inv;
+    }
+    if (mk && !(dd::ld<T>(mk + k) > 0.f)) v = 0.f;
+    dd::st<T>(out + k, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: out[t][cP][cQ] = sum_p P[p][cP] * Q[shift(p, t)][cQ]
+//   conv : P = dy (pivot grid = output grid), Q = x       -> dW[co][ci][t]
+//   convT: P = x  (pivot grid = input grid),  Q = dy      -> dW[ci][co][t]
+// shift(p, t) = p*s - pad + k*d (both cases).  grid = (taps, splits); thread (i, j) of a 16x16
+// layout owns cP in {i + 16a}, cQ in {j + 16b}; pixels staged 32 at a time through shared memory;
+// per-(split) partials, folded in order by wgrad_fold_kernel.
+// ------------------------------------------------------------------------------------------------
+struct WGeo {
+  int B, cP, cQ, Hp, Wp, Hq, Wq, kh, kw, sh, sw, ph, pw, dh, dw;
+  long long pix_per_split;
+};
+
+template <typename T, int TP, int TQ>
+__global__ void __launch_bounds__(256) conv2d_wgrad_kernel(const T* __restrict__ P, const T* __restrict__ Q,
+                                                           float* __restrict__ partial, WGeo g) {
+  constexpr int CH = 32;                       // pixels per stage
+  constexpr int PP = TP * 16, QQ = TQ * 16;
+  __shared__ float s_p[CH][PP + 1];
+  __shared__ float s_q[CH][QQ + 1];
+  const int tid = threadIdx.x, i = tid & 15, j = tid >> 4;
+  const int t = blockIdx.x, kh_i = t / g.kw, kw_i = t % g.kw;
+  const long long npix = (long long)g.B * g.Hp * g.Wp;
+  const long long p_begin = (long long)blockIdx.y * g.pix_per_split;
+  const long long p_end = p_begin + g.pix_per_split < npix ? p_begin + g.pix_per_split : npix;
+  float acc[TP][TQ];
+#pragma unroll
+  for (int a = 0; a < TP; ++a)
+#pragma unroll
+    for (int b = 0; b < TQ; ++b) acc[a][b] = 0.f;
+
+  for (long long p0 = p_begin; p0 < p_end; p0 += CH) {
+    __syncthreads();
+    for (int e = tid; e < CH * PP; e += 256) {
+      const int c = e % PP, l = e / PP;
+      const long long p = p0 + l;
+      s_p[l][c] = (p < p_end && c < g.cP) ? dd::ld<T>(P + (size_t)p * g.cP + c) : 0.f;
+    }
+    for (int e = tid; e < CH * QQ; e += 256) {
+      const int c = e % QQ, l = e / QQ;
+      const long long p = p0 + l;
+      float v = 0.f;
+      if (p < p_end && c < g.cQ) {
+        const int wp = (int)(p % g.Wp), hp = (int)((p / g.Wp) % g.Hp);
+        const long long b = p / ((long long)g.Wp * g.Hp);
+        const int hq = hp * g.sh - g.ph + kh_i * g.dh, wq = wp * g.sw - g.pw + kw_i * g.dw;
+        if (hq >= 0 && hq < g.Hq && wq >= 0 && wq < g.Wq)
+          v = dd::ld<T>(Q + (((size_t)b * g.Hq + hq) * g.Wq + wq) * g.cQ + c);
+      }
+      s_q[l][c] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int l = 0; l < CH; ++l) {
+      float pv[TP], qv[TQ];
+#pragma unroll
+      for (int a = 0; a < TP; ++a) pv[a] = s_p[l][i + 16 * a];
+#pragma unroll
+      for (int b = 0; b < TQ; ++b) qv[b] = s_q[l][j + 16 * b];
+#pragma unroll
+      for (int a = 0; a < TP; ++a)
+#pragma unroll
+        for (int b = 0; b < TQ; ++b) acc[a][b] = fmaf(pv[a], qv[b], acc[a][b]);
+    }
+  }
+  float* out = partial + ((size_t)blockIdx.y * gridDim.x + t) * g.cP * g.cQ;
+#pragma unroll
+  for (int a = 0; a < TP; ++a)
+#pragma unroll
+    for (int b = 0; b < TQ; ++b) {
+      const int cp = i + 16 * a, cq = j + 16 * b;
+      if (cp < g.cP && cq < g.cQ) out[cp * g.cQ + cq] = acc[a][b];
+    }
+}
+
+// dw[cP][cQ][t] = sum over splits (in order) of partial[split][t][cP][cQ]
+__global__ void wgrad_fold_kernel(const float* __restrict__ partial, float* __restrict__ dw, int taps, int cPQ, int splits) {
+  const int n = taps * cPQ;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int pq = e % cPQ, t = e / cPQ;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(size_t)k * n + e];
+    dw[(size_t)pq * taps + t] = s;
+  }
+}
+
+// db[c] = sum over pixels of dy[p][c]: per-CTA partials then an ordered fold
+template <typename T>
+__global__ void __launch_bounds__(256) chansum_kernel(const T* __restrict__ dy, long long npix, int Cn, float* __restrict__ partial) {
+  __shared__ float red[256];
+  const int tid = threadIdx.x;
+  const int lanes = 256 / Cn > 0 ? 256 / Cn : 1;     // pixel lanes per CTA (Cn <= 256)
+  const int c = tid % Cn, pl = tid / Cn;
+  float s = 0.f;
+  if (pl < lanes)
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes)
+      s += dd::ld<T>(dy + (size_t)p * Cn + c);
+  red[tid] = (pl < lanes) ? s : 0.f;
+  __syncthreads();
+  if (tid < Cn) {
+    float tsum = 0.f;
+    for (int l = 0; l < lanes; ++l) tsum += red[l * Cn + tid];
+    partial[(size_t)blockIdx.x * Cn + tid] = tsum;
+  }
+}
+__global__ void chansum_fold_kernel(const float* __restrict__ partial, int nblk, int Cn, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cn) return;
+  float s = 0.f;
+  for (int k = 0; k < nblk; ++k) s += partial[(size_t)k * Cn + c];
+  db[c] = s;
+}
+
+constexpr int kChanBlocks = dd::kSMs * 2;
+
+bool desc_ok(const dd_conv_desc* d) {
+  return d && d->B >= 0 && d->Cin > 0 && d->Cout > 0 && d->Hi > 0 && d->Wi > 0 && d->Ho > 0 && d->Wo > 0 && d->kh > 0 &&
+         d->kw > 0 && d->sh > 0 && d->sw > 0 && d->ph >= 0 && d->pw >= 0 && d->dh > 0 && d->dw > 0;
+}
+
+size_t wg_bytes(const dd_conv_desc* d) { return ((size_t)d->kh * d->kw * d->Cin * d->Cout * sizeof(float) + 255) / 256 * 256; }
+
+int wgrad_splits(const dd_conv_desc* d, long long npix) {
+  const int taps = d->kh * d->kw;
+  int s = (dd::kSMs * 4 + taps - 1) / taps;
+  const long long maxs = (npix + 255) / 256;
+  if (s > maxs) s = (int)maxs;
+  return s < 1 ? 1 : s;
+}
+
+template <typename T>
+int launch_gather(const T* x, const float* wg, const float* bias, const T* mask, T* y, const Geo& g, int act, cudaStream_t st) {
+  if (g.Ci > MAX_CI) return dd::fail(DD_ERR_UNSUPPORTED, "conv2d: %d input channels > %d", g.Ci, MAX_CI);
+  const long long npix = (long long)g.B * g.Ho * g.Wo;
+  if (g.Co > 16) {
+    dim3 grid((unsigned)((npix + 127) / 128), (g.Co + 31) / 32);
+    conv2d_gather_kernel<T, 32><<<grid, 256, 0, st>>>(x, wg, bias, mask, y, g, act);
+  } else {
+    dim3 grid((unsigned)((npix + 255) / 256), 1);
+    conv2d_gather_kernel<T, 16><<<grid, 256, 0, st>>>(x, wg, bias, mask, y, g, act);
+  }
+  return dd::check_launch("conv2d_gather");
+}
+
+template <typename T>
+int launch_wgrad(const T* P, const T* Q, float* partial, const WGeo& g, int taps, int splits, cudaStream_t st) {
+  dim3 grid(taps, splits);
+  const int tp = (g.cP + 15) / 16, tq = (g.cQ + 15) / 16;
+#define DD_WG(TPv, TQv) conv2d_wgrad_kernel<T, TPv, TQv><<<grid, 256, 0, st>>>(P, Q, partial, g)
+  if (tp <= 1 && tq <= 1) DD_WG(1, 1);
+  else if (tp <= 2 && tq <= 1) DD_WG(2, 1);
+  else if (tp <= 1 && tq <= 2) DD_WG(1, 2);
+  else if (tp <= 2 && tq <= 2) DD_WG(2, 2);
+  else if (tp <= 4 && tq <= 2) DD_WG(4, 2);
+  else if (tp <= 2 && tq <= 4) DD_WG(2, 4);
+  else if (tp <= 4 && tq <= 4) DD_WG(4, 4);
+  else if (tp <= 6 && tq <= 4) DD_WG(6, 4);
+  else if (tp <= 4 && tq <= 6) DD_WG(4, 6);
+  else return dd::fail(DD_ERR_UNSUPPORTED, "conv2d wgrad: channel tile %dx%d", g.cP, g.cQ);
+#undef DD_WG
+  return dd::check_launch("conv2d_wgrad");
+}
+}  // namespace
+
+extern "C" size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d) {
+  if (!desc_ok(d)) return 256;
+  const long long np_out = (long long)d->B * d->Ho * d->Wo, np_in = (long long)d->B * d->Hi * d->Wi;
+  const long long pivot = d->transposed ? np_in : np_out;
+  const size_t partial = (size_t)wgrad_splits(d, pivot) * d->kh * d->kw * d->Cin * d->Cout * sizeof(float);
+  const size_t chan = (size_t)kChanBlocks * d->Cout * sizeof(float);
+  const size_t a = wg_bytes(d), b = partial + chan;
+  return (a > b ? a : b) + 256;
+}
+
+extern "C" int dd_conv2d_fwd(const void* x, const float* w, const float* bias, void* y, const dd_conv_desc* d, int dtype,
+                             int act, void* workspace, size_t ws_bytes, void* stream) {
+  DD_REQUIRE(desc_ok(d), DD_ERR_BAD_ARG, "dd_conv2d_fwd: bad descriptor");
+  if (d->B == 0) return 0;
+  DD_REQUIRE(x && w && y && workspace, DD_ERR_BAD_ARG, "dd_conv2d_fwd: null pointer");
+  DD_REQUIRE(ws_bytes >= wg_bytes(d), DD_ERR_WORKSPACE, "dd_conv2d_fwd: workspace %zu < %zu", ws_bytes, wg_bytes(d));
+  DD_REQUIRE(act >= 0 && act <= 2, DD_ERR_BAD_ARG, "dd_conv2d_fwd: act %d", act);
+  cudaStream_t st = dd::as_stream(stream);
+  const int taps = d->kh * d->kw;
+  float* wg = (float*)workspace;
+  // conv weights are [Cout][Cin][t] (need wg[t][ci][co] = w[co][ci][t]: swap); convT weights are [Cin][Cout][t]
+  wprep_kernel<<<64, 256, 0, st>>>(w, wg, d->Cin, d->Cout, taps, d->transposed ? 0 : 1);
+  if (int e = dd::check_launch("conv2d_wprep")) return e;
+  Geo g{d->B, d->Cin, d->Cout, d->Hi, d->Wi, d->Ho, d->Wo, d->kh, d->kw, d->sh, d->sw, d->ph, d->pw, d->dh, d->dw, d->transposed};
+  if (dtype == DD_F32) return launch_gather<float>((const float*)x, wg, bias, nullptr, (float*)y, g, act, st);
+  if (dtype == DD_BF16)
+    return launch_gather<__nv_bfloat16>((const __nv_bfloat16*)x, wg, bias, nullptr, (__nv_bfloat16*)y, g, act, st);
+  return dd::fail(DD_ERR_UNSUPPORTED, "dd_conv2d_fwd: dtype %d", dtype);
+}
+
+extern "C" int dd_conv2d_dgrad(const void* dy, const float* w, const void* x_mask, void* dx, const dd_conv_desc* d, int dtype,
+                               void* workspace, size_t ws_bytes, void* stream) {
+  DD_REQUIRE(desc_ok(d), DD_ERR_BAD_ARG, "dd_conv2d_dgrad: bad descriptor");
+  if (d->B == 0) return 0;
+  DD_REQUIRE(dy && w && dx && workspace, DD_ERR_BAD_ARG, "dd_conv2d_dgrad: null pointer");
+  DD_REQUIRE(ws_bytes >= wg_bytes(d), DD_ERR_WORKSPACE, "dd_conv2d_dgrad: workspace %zu < %zu", ws_bytes, wg_bytes(d));
+  cudaStream_t st = dd::as_stream(stream);
+  const int taps = d->kh * d->kw;
+  float* wg = (float*)workspace;
+  // gathered tensor = dy (Cout channels), produced = dx (Cin channels): wg[t][co][ci]
+  wprep_kernel<<<64, 256, 0, st>>>(w, wg, d->Cout, d->Cin, taps, d->transposed ? 1 : 0);
+  if (int e = dd::check_launch("conv2d_wprep")) return e;
+  Geo g{d->B, d->Cout, d->Cin, d->Ho, d->Wo, d->Hi, d->Wi, d->kh, d->kw, d->sh, d->sw, d->ph, d->pw, d->dh, d->dw, !d->transposed};
+  if (dtype == DD_F32) return launch_gather<float>((const float*)dy, wg, nullptr, (const float*)x_mask, (float*)dx, g, 0, st);
+  if (dtype == DD_BF16)
+    return launch_gather<__nv_bfloat16>((const __nv_bfloat16*)dy, wg, nullptr, (const __nv_bfloat16*)x_mask, (__nv_bfloat16*)dx, g, 0, st);
+  return dd::fail(DD_ERR_UNSUPPORTED, "dd_conv2d_dgrad: dtype %d", dtype);
+}
+
+extern "C" int dd_conv2d_wgrad(const void* x, const void* dy, float* dw, float* db, const dd_conv_desc* d, int dtype,
+                               void* workspace, size_t ws_bytes, void* stream) {
+  DD_REQUIRE(desc_ok(d), DD_ERR_BAD_ARG, "dd_conv2d_wgrad: bad descriptor");
+  DD_REQUIRE(d->B > 0, DD_ERR_BAD_ARG, "dd_conv2d_wgrad: empty batch");
+  DD_REQUIRE(x && dy && dw && workspace, DD_ERR_BAD_ARG, "dd_conv2d_wgrad: null pointer");
+  DD_REQUIRE(ws_bytes >= dd_conv2d_workspace_bytes(d), DD_ERR_WORKSPACE, "dd_conv2d_wgrad: workspace %zu < %zu", ws_bytes,
+             dd_conv2d_workspace_bytes(d));
+  DD_REQUIRE(d->Cout <= 256, DD_ERR_UNSUPPORTED, "dd_conv2d_wgrad: Cout %d > 256", d->Cout);
+  cudaStream_t st = dd::as_stream(stream);
+  const int taps = d->kh * d->kw;
+  const long long np_out = (long long)d->B * d->Ho * d->Wo, np_in = (long long)d->B * d->Hi * d->Wi;
+  const long long pivot = d->transposed ? np_in : np_out;
+  const int splits = wgrad_splits(d, pivot);
+  WGeo g;
+  g.B = d->B;
+  g.kh = d->kh; g.kw = d->kw; g.sh = d->sh; g.sw = d->sw; g.ph = d->ph; g.pw = d->pw; g.dh = d->dh; g.dw = d->dw;
+  g.pix_per_split = ((pivot + splits - 1) / splits + 31) / 32 * 32;
+  const void *Pp, *Qp;
+  if (!d->transposed) { g.cP = d->Cout; g.cQ = d->Cin; g.Hp = d->Ho; g.Wp = d->Wo; g.Hq = d->Hi; g.Wq = d->Wi; Pp = dy; Qp = x; }
+  else { g.cP = d->Cin; g.cQ = d->Cout; g.Hp = d->Hi; g.Wp = d->Wi; g.Hq = d->Ho; g.Wq = d->Wo; Pp = x; Qp = dy; }
+  float* partial = (float*)workspace;
+  int e;
+  if (dtype == DD_F32) e = launch_wgrad<float>((const float*)Pp, (const float*)Qp, partial, g, taps, splits, st);
+  else if (dtype == DD_BF16) e = launch_wgrad<__nv_bfloat16>((const __nv_bfloat16*)Pp, (const __nv_bfloat16*)Qp, partial, g, taps, splits, st);
+  else return dd::fail(DD_ERR_UNSUPPORTED, "dd_conv2d_wgrad: dtype %d", dtype);
+  if (e) return e;
+  const int n = taps * d->Cin * d->Cout;
+  wgrad_fold_kernel<<<(n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184, 256, 0, st>>>(partial, dw, taps, d->Cin * d->Cout, splits);
+  if (int e2 = dd::check_launch("conv2d_wgrad_fold")) return e2;
+  if (db) {
+    float* cpart = partial + (size_t)splits * n;
+    const int lanes = 256 / d->Cout > 0 ? 256 / d->Cout : 1;
+    const long long want = (np_out + lanes - 1) / lanes;
+    const int nblk = (int)(want < kChanBlocks ? want : kChanBlocks);
+    if (dtype == DD_F32) chansum_kernel<float><<<nblk, 256, 0, st>>>((const float*)dy, np_out, d->Cout, cpart);
+    else chansum_kernel<__nv_bfloat16><<<nblk, 256, 0, st>>>((const __nv_bfloat16*)dy, np_out, d->Cout, cpart);
+    if (int e3 = dd::check_launch("conv2d_chansum")) return e3;
+    chansum_fold_kernel<<<(d->Cout + 255) / 256, 256, 0, st>>>(cpart, nblk, d->Cout, db);
+    return dd::check_launch("conv2d_chansum_fold");
+  }
+  return 0;
+}

@@ -415,7 +415,7 @@ __global__ void c1_wgrad_reduce_kernel(const float* __restrict__ partial, int nb
 
 template <typename T>
 __global__ void relu_mask_kernel(const T* __restrict__ g, const T* __restrict__ act, T* __restrict__ out,
-                                 long long n8) {
+                                 long long n8, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8];
     dd::ld8<T>(g + i * 8, a);
@@ -424,6 +424,10 @@ __global__ void relu_mask_kernel(const T* __restrict__ g, const T* __restrict__ 
     for (int k = 0; k < 8; ++k) a[k] = b[k] > 0.f ? a[k] : 0.f;
     dd::st8<T>(out + i * 8, a);
   }
+  // ragged tail (n % 8), first CTA
+  if (blockIdx.x == 0)
+    for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x)
+      dd::st<T>(out + i, dd::ld<T>(act + i) > 0.f ? dd::ld<T>(g + i) : 0.f);
 }
 
 constexpr int kWgradBlocks = dd::kSMs * 2;
@@ -632,15 +636,17 @@ extern "C" int dd_conv_c1_wgrad(const float* in, int in_is_views, const void* dy
 }
 
 extern "C" int dd_relu_mask(const void* g, const void* act, void* out, int dtype, long long n, void* stream) {
-  DD_REQUIRE(g && act && out, DD_ERR_BAD_ARG, "dd_relu_mask: null pointer");
-  DD_REQUIRE(n >= 0 && n % 8 == 0, DD_ERR_BAD_ARG, "dd_relu_mask: n=%lld must be a multiple of 8", n);
+  DD_REQUIRE(n >= 0, DD_ERR_BAD_ARG, "dd_relu_mask: n=%lld", n);
   if (n == 0) return 0;
+  DD_REQUIRE(g && act && out, DD_ERR_BAD_ARG, "dd_relu_mask: null pointer");
   const long long n8 = n / 8;
-  const int grid = (int)((n8 + 255) / 256 < dd::kSMs * 8 ? (n8 + 255) / 256 : dd::kSMs * 8);
+  long long want = (n8 + 255) / 256;
+  if (want < 1) want = 1;
+  const int grid = (int)(want < dd::kSMs * 8 ? want : dd::kSMs * 8);
   cudaStream_t st = dd::as_stream(stream);
-  if (dtype == DD_F32) relu_mask_kernel<float><<<grid, 256, 0, st>>>((const float*)g, (const float*)act, (float*)out, n8);
+  if (dtype == DD_F32) relu_mask_kernel<float><<<grid, 256, 0, st>>>((const float*)g, (const float*)act, (float*)out, n8, n);
   else if (dtype == DD_BF16)
-    relu_mask_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)act, (__nv_bfloat16*)out, n8);
+    relu_mask_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)act, (__nv_bfloat16*)out, n8, n);
   else return dd::fail(DD_ERR_UNSUPPORTED, "dd_relu_mask: dtype %d", dtype);
   return dd::check_launch("relu_mask");
 }

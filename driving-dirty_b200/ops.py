@@ -368,7 +368,148 @@ def mse_loss(y, y_hat):
     return MseLoss.apply(y, y_hat)
 
 
-def decoder_deconv_stack(x, dc1, dc2, dc3, dc4):
-    """Decoder transposed-conv stack (components.py:88-92).  Kernels not built yet in this round;
-    fails loudly rather than falling back to a library path."""
-    raise RuntimeError("decoder transposed-conv kernels are not built yet (BasicAE decode path, SURVEY A13)")
+# --------------------------------------------------------------------------------------------
+# generic conv / transposed conv on NHWC activations (decoder, bounding-box CNNs)
+# --------------------------------------------------------------------------------------------
+def _pair(v):
+    return (int(v), int(v)) if not isinstance(v, (tuple, list)) else (int(v[0]), int(v[1]))
+
+
+def conv_out_size(hi, k, s, p, d, transposed, output_padding=0):
+    if transposed:
+        return (hi - 1) * s - 2 * p + d * (k - 1) + output_padding + 1
+    return (hi + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def _conv_desc(B, Cin, Cout, Hi, Wi, Ho, Wo, k, s, p, d, transposed):
+    return _lib.ConvDesc(B, Cin, Cout, Hi, Wi, Ho, Wo, k[0], k[1], s[0], s[1], p[0], p[1], d[0], d[1], int(transposed))
+
+
+def _conv2d_ws(desc, device):
+    import ctypes
+    n = int(_lib.load().dd_conv2d_workspace_bytes(ctypes.byref(desc)))
+    return _ws.get("conv2d", n, device), n
+
+
+class LayoutToNHWC(torch.autograd.Function):
+    """NCHW fp32 (API edge) -> NHWC activation of ``dtype``."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        _require_cuda(x)
+        x = _c(x.float())
+        B, Cn, H, W = x.shape
+        out = torch.empty(B, H, W, Cn, dtype=dtype, device=x.device)
+        call("dd_nchw_f32_to_nhwc", x.data_ptr(), out.data_ptr(), dtype_code(dtype), B, Cn, H, W, stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        B, H, W, Cn = g.shape
+        out = torch.empty(B, Cn, H, W, dtype=torch.float32, device=g.device)
+        call("dd_nhwc_to_nchw_f32", g.data_ptr(), dtype_code(g.dtype), out.data_ptr(), B, Cn, H, W, stream_ptr())
+        return out, None
+
+
+class LayoutToNCHW(torch.autograd.Function):
+    """NHWC activation -> NCHW fp32 (API edge)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        x = _c(x)
+        ctx.dtype = x.dtype
+        B, H, W, Cn = x.shape
+        out = torch.empty(B, Cn, H, W, dtype=torch.float32, device=x.device)
+        call("dd_nhwc_to_nchw_f32", x.data_ptr(), dtype_code(x.dtype), out.data_ptr(), B, Cn, H, W, stream_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g.float())
+        B, Cn, H, W = g.shape
+        out = torch.empty(B, H, W, Cn, dtype=ctx.dtype, device=g.device)
+        call("dd_nchw_f32_to_nhwc", g.data_ptr(), out.data_ptr(), dtype_code(ctx.dtype), B, Cn, H, W, stream_ptr())
+        return out
+
+
+def to_nhwc(x, dtype=torch.float32):
+    return LayoutToNHWC.apply(x, dtype)
+
+
+def to_nchw(x):
+    return LayoutToNCHW.apply(x)
+
+
+class Conv2dNHWC(torch.autograd.Function):
+    """nn.Conv2d / nn.ConvTranspose2d (+ bias, + optional ReLU) on an NHWC activation [B,H,W,Cin] of
+    fp32 or bf16; weight / bias fp32 in torch layout.  geom = (kernel, stride, padding, dilation,
+    transposed, output_padding), pairs like torch's."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, geom, relu):
+        import ctypes
+        _require_cuda(x, weight)
+        k, s, p, d, transposed, opad = geom
+        x = _c(x)
+        w = _c(weight.detach().float())
+        B, Hi, Wi, Cin = x.shape
+        Cout = w.shape[1] if transposed else w.shape[0]
+        if (w.shape[0] if transposed else w.shape[1]) != Cin:
+            raise RuntimeError(f"conv2d: input has {Cin} channels, weight {tuple(w.shape)}")
+        Ho = conv_out_size(Hi, k[0], s[0], p[0], d[0], transposed, opad[0])
+        Wo = conv_out_size(Wi, k[1], s[1], p[1], d[1], transposed, opad[1])
+        desc = _conv_desc(B, Cin, Cout, Hi, Wi, Ho, Wo, k, s, p, d, transposed)
+        y = torch.empty(B, Ho, Wo, Cout, dtype=x.dtype, device=x.device)
+        ws, n = _conv2d_ws(desc, x.device)
+        bptr = _c(bias.detach().float()).data_ptr() if bias is not None else None
+        call("dd_conv2d_fwd", x.data_ptr(), w.data_ptr(), bptr, y.data_ptr(), ctypes.byref(desc), dtype_code(x.dtype),
+             1 if relu else 0, ws.data_ptr(), n, stream_ptr())
+        ctx.desc, ctx.relu, ctx.has_bias = desc, relu, bias is not None
+        ctx.save_for_backward(x, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes
+        x, w, y = ctx.saved_tensors
+        desc, st, code = ctx.desc, stream_ptr(), dtype_code(x.dtype)
+        dy = _c(dy.to(x.dtype))
+        if ctx.relu:
+            dym = torch.empty_like(dy)
+            call("dd_relu_mask", dy.data_ptr(), y.data_ptr(), dym.data_ptr(), code, dy.numel(), st)
+            dy = dym
+        ws, n = _conv2d_ws(desc, x.device)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("dd_conv2d_dgrad", dy.data_ptr(), w.data_ptr(), None, dx.data_ptr(), ctypes.byref(desc), code,
+                 ws.data_ptr(), n, st)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            db = torch.empty(desc.Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            call("dd_conv2d_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr() if db is not None else None,
+                 ctypes.byref(desc), code, ws.data_ptr(), n, st)
+        return dx, dw, db, None, None
+
+
+def conv2d_nhwc(x, module, relu=False):
+    """Apply an nn.Conv2d / nn.ConvTranspose2d parameter container to an NHWC activation."""
+    transposed = isinstance(module, torch.nn.ConvTranspose2d)
+    geom = (_pair(module.kernel_size), _pair(module.stride), _pair(module.padding), _pair(module.dilation), transposed,
+            _pair(module.output_padding) if transposed else (0, 0))
+    if module.groups != 1:
+        raise RuntimeError("conv2d_nhwc: grouped convolutions are not part of the scene pipeline")
+    return Conv2dNHWC.apply(x, module.weight, module.bias, geom, bool(relu))
+
+
+def decoder_deconv_stack(x, dc1, dc2, dc3, dc4, act_dtype=torch.float32):
+    """Decoder transposed-conv stack (components.py:88-92): x [B,64,h,w] NCHW fp32 ->
+    relu(dc1) -> relu(dc2) -> relu(dc3, k2 s2) -> dc4 (1x1) -> [B,3,2h,2w] NCHW fp32."""
+    a = to_nhwc(x, act_dtype)
+    a = conv2d_nhwc(a, dc1, relu=True)
+    a = conv2d_nhwc(a, dc2, relu=True)
+    a = conv2d_nhwc(a, dc3, relu=True)
+    a = conv2d_nhwc(a, dc4, relu=False)
+    return to_nchw(a)

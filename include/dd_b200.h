@@ -131,6 +131,27 @@ size_t dd_bce_ts_workspace_bytes(void);
 int dd_threat_score_f32(const float* a, const float* b, float* ts, void* workspace,
                         size_t ws_bytes, long long n, void* stream);
 
+/* ---- A13/A15/A16: generic conv / transposed conv (any kernel, stride, padding, dilation) ------
+ * Decoder dc1..dc4 (components.py:70-73,89-92); SpatialMappingCNN and RoadMapBoxesMergingCNN layers
+ * (spatial_bb/components.py:18-26,129-139).  The descriptor states the FORWARD layer for all three
+ * passes: x NHWC [B,Hi,Wi,Cin] -> y NHWC [B,Ho,Wo,Cout]; transposed = 1 for nn.ConvTranspose2d.
+ * Weights fp32 in torch layout (Conv2d [Cout,Cin,kh,kw]; ConvTranspose2d [Cin,Cout,kh,kw]).
+ * act: 0 none, 1 ReLU, 2 sigmoid (fused after the bias).  dgrad: dx = gather(dy, w) * (x_mask > 0),
+ * x_mask may be NULL; dy must already carry this layer's own activation derivative.
+ * wgrad: dw (torch layout), db (may be NULL); deterministic ordered reductions. */
+typedef struct {
+  int B, Cin, Cout, Hi, Wi, Ho, Wo;
+  int kh, kw, sh, sw, ph, pw, dh, dw;
+  int transposed;
+} dd_conv_desc;
+int dd_conv2d_fwd(const void* x, const float* w, const float* bias, void* y, const dd_conv_desc* d,
+                  int dtype, int act, void* workspace, size_t ws_bytes, void* stream);
+int dd_conv2d_dgrad(const void* dy, const float* w, const void* x_mask, void* dx,
+                    const dd_conv_desc* d, int dtype, void* workspace, size_t ws_bytes, void* stream);
+int dd_conv2d_wgrad(const void* x, const void* dy, float* dw, float* db, const dd_conv_desc* d,
+                    int dtype, void* workspace, size_t ws_bytes, void* stream);
+size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d);
+
 /* ---- A14: mean squared error (autoencoder.py:91) ---------------------------------------------*/
 int dd_mse_fwd(const float* y, const float* y_hat, float* loss, void* workspace, size_t ws_bytes,
                long long n, void* stream);

@@ -374,3 +374,60 @@ def test_threat_score_and_mse(dd):
     ld = dd.mse_loss(y.cuda(), yhd)
     ld.backward()
     assert abs(float(ld) - float(lr)) < 1e-6 and rel_max_err(yhd.grad, yhr.grad) < 1e-6
+
+
+# ------------------------------------------------------------------------------- generic conv --
+# one case per layer TYPE of the decoder (components.py:70-73) and of the bounding-box CNNs
+# (spatial_bb/components.py:18-26,129-139), at reduced spatial size
+GENERIC_LAYERS = {
+    "dc1_convT_64_32_k3p1": dict(t=True, cin=64, cout=32, k=3, s=1, p=1, d=1, hw=(9, 11)),
+    "dc3_convT_32_32_k2s2": dict(t=True, cin=32, cout=32, k=2, s=2, p=0, d=1, hw=(8, 10)),
+    "dc4_convT_32_3_k1": dict(t=True, cin=32, cout=3, k=1, s=1, p=0, d=1, hw=(16, 20)),
+    "strip_conv_3_32_1x50_s32": dict(t=False, cin=3, cout=32, k=(1, 50), s=(3, 2), p=0, d=1, hw=(20, 70)),
+    "strip_conv_3_32_52x1_s32_p1": dict(t=False, cin=3, cout=32, k=(52, 1), s=(3, 2), p=1, d=1, hw=(64, 18)),
+    "out_conv_32_32_k3_valid": dict(t=False, cin=32, cout=32, k=3, s=1, p=0, d=1, hw=(12, 13)),
+    "rm_conv2_32_32_k3_d3": dict(t=False, cin=32, cout=32, k=3, s=1, p=0, d=3, hw=(14, 15)),
+    "ss_conv_32_32_1x24_s17": dict(t=False, cin=32, cout=32, k=(1, 24), s=(1, 7), p=0, d=1, hw=(5, 66)),
+    "rm_conv1_1_32_k7s3d3p1": dict(t=False, cin=1, cout=32, k=7, s=3, p=1, d=3, hw=(40, 43)),
+    "up_conv1_convT_96_64_k7d7": dict(t=True, cin=96, cout=64, k=7, s=1, p=0, d=7, hw=(6, 7)),
+    "up_conv4_convT_16_8_k7d3": dict(t=True, cin=16, cout=8, k=7, s=1, p=0, d=3, hw=(9, 8)),
+    "up_conv5_convT_8_1_k2s2": dict(t=True, cin=8, cout=1, k=2, s=2, p=0, d=1, hw=(10, 11)),
+}
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("layer", sorted(GENERIC_LAYERS))
+@pytest.mark.parametrize("relu", [False, True])
+def test_conv2d_generic_fwd_dgrad_wgrad(dd, layer, dtype, tol, relu):
+    """dd_conv2d_fwd / dgrad / wgrad against torch's CPU conv2d / conv_transpose2d and autograd."""
+    L = GENERIC_LAYERS[layer]
+    B = 2
+    g = torch.Generator().manual_seed(sum(map(ord, layer)))
+    mod_cls = torch.nn.ConvTranspose2d if L["t"] else torch.nn.Conv2d
+    mod = mod_cls(L["cin"], L["cout"], kernel_size=L["k"], stride=L["s"], padding=L["p"], dilation=L["d"])
+    x = q(torch.randn(B, L["cin"], *L["hw"], generator=g), dtype).requires_grad_(True)
+    y = mod(x)
+    if relu:
+        y = F.relu(y)
+    dy = q(torch.randn(y.shape, generator=g), dtype)
+    y.backward(dy)
+    # device
+    m2 = mod_cls(L["cin"], L["cout"], kernel_size=L["k"], stride=L["s"], padding=L["p"], dilation=L["d"]).cuda()
+    m2.load_state_dict(mod.state_dict())
+    xd = nhwc(x.detach(), dtype).requires_grad_(True)
+    yd = dd.conv2d_nhwc(xd, m2, relu=relu)
+    assert tuple(yd.shape) == (B, y.shape[2], y.shape[3], L["cout"])
+    assert rel_max_err(to_nchw(yd.detach()), y) < tol
+    yd.backward(nhwc(dy, dtype))
+    assert rel_max_err(to_nchw(xd.grad), x.grad) < tol
+    assert rel_max_err(m2.weight.grad, mod.weight.grad) < tol
+    assert rel_max_err(m2.bias.grad, mod.bias.grad) < tol
+
+
+def test_relu_mask_ragged_tail(dd):
+    from driving_dirty_b200._lib import call, stream_ptr
+    g = torch.randn(1003, device="cuda")
+    a = torch.randn(1003, device="cuda")
+    out = torch.empty_like(g)
+    call("dd_relu_mask", g.data_ptr(), a.data_ptr(), out.data_ptr(), 0, 1003, stream_ptr())
+    assert torch.equal(out, g * (a > 0))

@@ -231,3 +231,70 @@ def test_encoder_mosaic_entry_and_c3_only(golden):
         enc.c3_only = False
     _, _, a3 = so.encoder_convs(params, so.stitch(views))
     assert ssr.shape == a3.shape and rel_max_err(ssr, a3) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# BasicAE (config 3): six_to_one_task -> encoder -> decoder -> MSE, against the golden written from
+# the unmodified reference (tests/golden/ae_small.pt) and the oracle
+# ------------------------------------------------------------------------------------------------
+def _ae_model(g, dtype="fp32"):
+    from driving_dirty_b200.autoencoder.autoencoder import BasicAE, default_hparams
+    hp = default_hparams(hidden_dim=g["hidden"], latent_dim=g["latent"], input_width=6 * g["view_w"],
+                         input_height=g["view_h"], output_width=g["view_w"], output_height=g["view_h"],
+                         compute_dtype=dtype)
+    ae = BasicAE(hp)
+    ae.load_state_dict(g["state_dict"])
+    return ae.cuda().train()
+
+
+def test_ae_train_step_fp32_against_golden(golden):
+    import numpy as np
+    g = golden("ae_small")
+    ae = _ae_model(g)
+    views, _ = so.synthetic_scene_batch(g["batch"], g["view_h"], g["view_w"], map_hw=8, seed=777)
+    with cpu_rng_dropout():
+        np.random.seed(4321)                      # six_to_one_task draws the slot from the host RNG
+        torch.manual_seed(99)
+        x, y = ae.six_to_one_task(views.cuda())
+        z = ae.encoder(x)
+        y_hat = ae(z)
+        from driving_dirty_b200 import ops
+        loss = ops.mse_loss(y, y_hat)
+        loss.backward()
+    xo, yo = so.six_to_one(views, g["slot"])
+    assert torch.equal(x.cpu(), xo) and torch.equal(y.cpu(), yo)
+    assert rel_max_err(z, g["z"]) < 1e-5
+    assert rel_max_err(y_hat, g["y_hat"]) < 1e-5
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5 * max(1.0, float(g["loss"]))
+    # gradients: B = 3 batch-statistics BatchNorm (x4 on the way back) amplifies fp32 summation-order
+    # noise ~10x (same effect as in test_full_size_train_bf16's note); 5e-4 of max|ref| per tensor
+    big = max(g["grad_norm"].values())
+    worst = {}
+    for k, p in ae.named_parameters():
+        ref = g["grad_sample"][k]
+        got = so.strided_sample(p.grad.cpu(), 512)
+        if g["grad_norm"][k] < 1e-5 * big:        # a bias feeding BatchNorm: true gradient 0, compare absolutely
+            worst[k] = (float((got - ref).abs().max()) / (1e-5 * big) * 5e-4, 0.0)
+            continue
+        scale = float(ref.abs().max())
+        worst[k] = (float((got - ref).abs().max()) / scale,
+                    abs(float(p.grad.double().norm()) - g["grad_norm"][k]) / g["grad_norm"][k])
+    print("\n".join(f"{k:32s} sample rel-max {a:.2e} norm rel {b:.2e}" for k, (a, b) in worst.items()))
+    bad = {k: v for k, v in worst.items() if v[0] > 5e-4 or v[1] > 5e-4}
+    assert not bad, bad
+
+
+def test_ae_run_step_matches_oracle_bf16(golden):
+    """bf16 activation storage in the decoder / encoder conv stacks: loss within 1e-2, y_hat within
+    1e-2 of max|ref| against the fp32 reference path."""
+    import numpy as np
+    g = golden("ae_small")
+    ae = _ae_model(g, "bf16")
+    views, _ = so.synthetic_scene_batch(g["batch"], g["view_h"], g["view_w"], map_hw=8, seed=777)
+    with cpu_rng_dropout():
+        np.random.seed(4321)
+        torch.manual_seed(99)
+        loss = ae._run_step(views.cuda(), 0, "train")
+        loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-2 * max(1.0, float(g["loss"]))
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ae.parameters())
