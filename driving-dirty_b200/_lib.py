@@ -50,6 +50,12 @@ SIGNATURES = {
     "dd_conv2d_dgrad": (_I, [_P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "dd_conv2d_wgrad": (_I, [_P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "dd_conv2d_workspace_bytes": (_Z, [_P]),
+    "dd_view_extract": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "dd_nhwc_place": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "dd_sigmoid_bwd": (_I, [_P, _P, _P, _I, _L, _P]),
+    "dd_bce_prob_fwd": (_I, [_P, _P, _P, _P, _Z, _L, _P]),
+    "dd_bce_prob_bwd": (_I, [_P, _P, _P, _P, _L, _P]),
+    "dd_bce_prob_workspace_bytes": (_Z, []),
     "dd_mse_fwd": (_I, [_P, _P, _P, _P, _Z, _L, _P]),
     "dd_mse_bwd": (_I, [_P, _P, _P, _P, _L, _P]),
 }

@@ -226,31 +226,32 @@ __global__ void wgrad_fold_kernel(const float* __restrict__ partial, float* __re
   }
 }
 
-// db[c] = sum over pixels of dy[p][c]: per-CTA partials then an ordered fold
+// db[c] = sum over pixels of dy[p][c]: per-CTA partials then an ordered fold.  Accumulated in double:
+// a bias gradient is a long mixed-sign sum ((p - t)/N terms) and fp32 partials lose ~1e-4 of it.
 template <typename T>
-__global__ void __launch_bounds__(256) chansum_kernel(const T* __restrict__ dy, long long npix, int Cn, float* __restrict__ partial) {
-  __shared__ float red[256];
+__global__ void __launch_bounds__(256) chansum_kernel(const T* __restrict__ dy, long long npix, int Cn, double* __restrict__ partial) {
+  __shared__ double red[256];
   const int tid = threadIdx.x;
   const int lanes = 256 / Cn > 0 ? 256 / Cn : 1;     // pixel lanes per CTA (Cn <= 256)
   const int c = tid % Cn, pl = tid / Cn;
-  float s = 0.f;
+  double s = 0.0;
   if (pl < lanes)
     for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes)
-      s += dd::ld<T>(dy + (size_t)p * Cn + c);
-  red[tid] = (pl < lanes) ? s : 0.f;
+      s += (double)dd::ld<T>(dy + (size_t)p * Cn + c);
+  red[tid] = (pl < lanes) ? s : 0.0;
   __syncthreads();
   if (tid < Cn) {
-    float tsum = 0.f;
+    double tsum = 0.0;
     for (int l = 0; l < lanes; ++l) tsum += red[l * Cn + tid];
     partial[(size_t)blockIdx.x * Cn + tid] = tsum;
   }
 }
-__global__ void chansum_fold_kernel(const float* __restrict__ partial, int nblk, int Cn, float* __restrict__ db) {
+__global__ void chansum_fold_kernel(const double* __restrict__ partial, int nblk, int Cn, float* __restrict__ db) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
-  float s = 0.f;
+  double s = 0.0;
   for (int k = 0; k < nblk; ++k) s += partial[(size_t)k * Cn + c];
-  db[c] = s;
+  db[c] = (float)s;
 }
 
 constexpr int kChanBlocks = dd::kSMs * 2;
@@ -309,7 +310,7 @@ extern "C" size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d) {
   const long long np_out = (long long)d->B * d->Ho * d->Wo, np_in = (long long)d->B * d->Hi * d->Wi;
   const long long pivot = d->transposed ? np_in : np_out;
   const size_t partial = (size_t)wgrad_splits(d, pivot) * d->kh * d->kw * d->Cin * d->Cout * sizeof(float);
-  const size_t chan = (size_t)kChanBlocks * d->Cout * sizeof(float);
+  const size_t chan = (size_t)kChanBlocks * d->Cout * sizeof(double) + 8;
   const size_t a = wg_bytes(d), b = partial + chan;
   return (a > b ? a : b) + 256;
 }
@@ -383,7 +384,7 @@ extern "C" int dd_conv2d_wgrad(const void* x, const void* dy, float* dw, float* 
   wgrad_fold_kernel<<<(n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184, 256, 0, st>>>(partial, dw, taps, d->Cin * d->Cout, splits);
   if (int e2 = dd::check_launch("conv2d_wgrad_fold")) return e2;
   if (db) {
-    float* cpart = partial + (size_t)splits * n;
+    double* cpart = reinterpret_cast<double*>(((uintptr_t)(partial + (size_t)splits * n) + 7) & ~(uintptr_t)7);
     const int lanes = 256 / d->Cout > 0 ? 256 / d->Cout : 1;
     const long long want = (np_out + lanes - 1) / lanes;
     const int nblk = (int)(want < kChanBlocks ? want : kChanBlocks);
@@ -394,4 +395,171 @@ extern "C" int dd_conv2d_wgrad(const void* x, const void* dy, float* dw, float* 
     return dd::check_launch("conv2d_chansum_fold");
   }
   return 0;
+}
+
+// ================================================================================================
+// Data movement around the bounding-box CNNs (spatial_bb/components.py:34-73,156) and the prob-space
+// loss of spatial_w_rm.py:128-131.
+// ================================================================================================
+namespace {
+
+// one camera of each scene as an NHWC image, with the rot90 / flip of SpatialMappingCNN.forward folded
+// into the indexing.  mode 0: as is; 1: rot90(k=1,[2,3]) out[i,j] = x[j, W-1-i]; 2: rot90(k=1,[3,2])
+// out[i,j] = x[H-1-j, i]; 3: flip([2,3]) out[i,j] = x[H-1-i, W-1-j].  views fp32 [B,6,3,H,W].
+template <typename T>
+__global__ void view_extract_kernel(const float* __restrict__ views, T* __restrict__ out, int B, int H, int W, int view,
+                                    int mode, int Ho, int Wo) {
+  const long long total = (long long)B * Ho * Wo * 3;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % 3);
+    const int j = (int)((idx / 3) % Wo);
+    const int i = (int)((idx / (3LL * Wo)) % Ho);
+    const long long b = idx / (3LL * Wo * Ho);
+    int h, w;
+    if (mode == 0) { h = i; w = j; }
+    else if (mode == 1) { h = j; w = W - 1 - i; }
+    else if (mode == 2) { h = H - 1 - j; w = i; }
+    else { h = H - 1 - i; w = W - 1 - j; }
+    dd::st<T>(out + idx, __ldg(views + (((b * 6 + view) * 3 + c) * H + h) * (size_t)W + w));
+  }
+}
+
+// dir 0: big[b, oy+i, ox+j, oc+k] = small[b,i,j,k];  dir 1: small[b,i,j,k] = big[b, oy+i, ox+j, oc+k]
+template <typename T>
+__global__ void nhwc_place_kernel(T* __restrict__ small_, T* __restrict__ big, int B, int h, int w, int c, int H, int W,
+                                  int C, int oy, int ox, int oc, int dir) {
+  const long long total = (long long)B * h * w * c;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % c);
+    const int j = (int)((idx / c) % w);
+    const int i = (int)((idx / ((long long)c * w)) % h);
+    const long long b = idx / ((long long)c * w * h);
+    const size_t o = (((size_t)b * H + oy + i) * W + ox + j) * C + oc + k;
+    if (dir == 0) big[o] = small_[idx];
+    else small_[idx] = big[o];
+  }
+}
+
+// dpre = dy * (1 - y) * y   (torch's sigmoid backward)
+template <typename T>
+__global__ void sigmoid_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float yy = dd::ld<T>(y + i);
+    dd::st<T>(out + i, dd::ld<T>(dy + i) * (1.0f - yy) * yy);
+  }
+}
+
+// F.binary_cross_entropy(p, t) (spatial_w_rm.py:131): -(t * max(log p, -100) + (1-t) * max(log(1-p), -100)), mean
+struct BceProbWs {
+  double partial[dd::kSMs * 4];
+  unsigned int ticket, pad[3];
+};
+__global__ void __launch_bounds__(256) bce_prob_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                                       float* __restrict__ loss, BceProbWs* __restrict__ ws, long long n) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float pv = p[i], tv = t[i];
+    s -= tv * fmaxf(logf(pv), -100.f) + (1.0f - tv) * fmaxf(log1pf(-pv), -100.f);
+  }
+  __shared__ double red[8];
+  double v = dd::warp_sum((double)s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += red[k];
+    ws->partial[blockIdx.x] = tot;
+    __threadfence();
+    last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  double tot = 0.0;
+  for (unsigned int k = 0; k < gridDim.x; ++k) tot += __ldcg(&ws->partial[k]);
+  loss[0] = (float)(tot / (double)n);
+  ws->ticket = 0;
+}
+// dp = g * (p - t) / max((1 - p) * p, 1e-12) / n   (aten's binary_cross_entropy_backward, mean reduction)
+__global__ void bce_prob_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ g,
+                                    float* __restrict__ dp, long long n) {
+  const float go = g ? __ldg(g) : 1.0f;
+  const float fn = (float)n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    dp[i] = __fdiv_rn(__fdiv_rn(go * (pv - t[i]), fmaxf((1.0f - pv) * pv, 1e-12f)), fn);
+  }
+}
+
+int grid_elems(long long total) {
+  long long g = (total + 255) / 256;
+  return (int)(g < 1 ? 1 : (g < dd::kSMs * 16 ? g : dd::kSMs * 16));
+}
+}  // namespace
+
+extern "C" int dd_view_extract(const float* views, void* out, int out_dtype, int B, int H, int W, int view, int mode,
+                               void* stream) {
+  DD_REQUIRE(B >= 0 && H > 0 && W > 0, DD_ERR_BAD_ARG, "dd_view_extract: bad shape");
+  DD_REQUIRE(view >= 0 && view < 6 && mode >= 0 && mode <= 3, DD_ERR_BAD_ARG, "dd_view_extract: view %d mode %d", view, mode);
+  if (B == 0) return 0;
+  DD_REQUIRE(views && out, DD_ERR_BAD_ARG, "dd_view_extract: null pointer");
+  const bool rot = mode == 1 || mode == 2;
+  const int Ho = rot ? W : H, Wo = rot ? H : W;
+  const long long total = (long long)B * Ho * Wo * 3;
+  cudaStream_t st = dd::as_stream(stream);
+  if (out_dtype == DD_F32) view_extract_kernel<float><<<grid_elems(total), 256, 0, st>>>(views, (float*)out, B, H, W, view, mode, Ho, Wo);
+  else if (out_dtype == DD_BF16)
+    view_extract_kernel<__nv_bfloat16><<<grid_elems(total), 256, 0, st>>>(views, (__nv_bfloat16*)out, B, H, W, view, mode, Ho, Wo);
+  else return dd::fail(DD_ERR_UNSUPPORTED, "dd_view_extract: dtype %d", out_dtype);
+  return dd::check_launch("view_extract");
+}
+
+extern "C" int dd_nhwc_place(void* small_, void* big, int dtype, int B, int h, int w, int c, int H, int W, int C, int oy,
+                             int ox, int oc, int dir, void* stream) {
+  DD_REQUIRE(B >= 0 && h > 0 && w > 0 && c > 0, DD_ERR_BAD_ARG, "dd_nhwc_place: bad shape");
+  DD_REQUIRE(oy >= 0 && ox >= 0 && oc >= 0 && oy + h <= H && ox + w <= W && oc + c <= C, DD_ERR_BAD_ARG,
+             "dd_nhwc_place: window [%d+%d, %d+%d, %d+%d] outside [%d,%d,%d]", oy, h, ox, w, oc, c, H, W, C);
+  if (B == 0) return 0;
+  DD_REQUIRE(small_ && big, DD_ERR_BAD_ARG, "dd_nhwc_place: null pointer");
+  const long long total = (long long)B * h * w * c;
+  cudaStream_t st = dd::as_stream(stream);
+  if (dtype == DD_F32) nhwc_place_kernel<float><<<grid_elems(total), 256, 0, st>>>((float*)small_, (float*)big, B, h, w, c, H, W, C, oy, ox, oc, dir);
+  else if (dtype == DD_BF16)
+    nhwc_place_kernel<__nv_bfloat16><<<grid_elems(total), 256, 0, st>>>((__nv_bfloat16*)small_, (__nv_bfloat16*)big, B, h, w, c, H, W, C, oy, ox, oc, dir);
+  else return dd::fail(DD_ERR_UNSUPPORTED, "dd_nhwc_place: dtype %d", dtype);
+  return dd::check_launch("nhwc_place");
+}
+
+extern "C" int dd_sigmoid_bwd(const void* dy, const void* y, void* out, int dtype, long long n, void* stream) {
+  DD_REQUIRE(n >= 0, DD_ERR_BAD_ARG, "dd_sigmoid_bwd: n=%lld", n);
+  if (n == 0) return 0;
+  DD_REQUIRE(dy && y && out, DD_ERR_BAD_ARG, "dd_sigmoid_bwd: null pointer");
+  cudaStream_t st = dd::as_stream(stream);
+  if (dtype == DD_F32) sigmoid_bwd_kernel<float><<<grid_elems(n), 256, 0, st>>>((const float*)dy, (const float*)y, (float*)out, n);
+  else if (dtype == DD_BF16)
+    sigmoid_bwd_kernel<__nv_bfloat16><<<grid_elems(n), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)out, n);
+  else return dd::fail(DD_ERR_UNSUPPORTED, "dd_sigmoid_bwd: dtype %d", dtype);
+  return dd::check_launch("sigmoid_bwd");
+}
+
+extern "C" size_t dd_bce_prob_workspace_bytes(void) { return sizeof(BceProbWs); }
+
+extern "C" int dd_bce_prob_fwd(const float* probs, const float* target, float* loss, void* workspace, size_t ws_bytes,
+                               long long n, void* stream) {
+  DD_REQUIRE(probs && target && loss && workspace, DD_ERR_BAD_ARG, "dd_bce_prob_fwd: null pointer");
+  DD_REQUIRE(n > 0, DD_ERR_BAD_ARG, "dd_bce_prob_fwd: n=%lld", n);
+  DD_REQUIRE(ws_bytes >= sizeof(BceProbWs), DD_ERR_WORKSPACE, "dd_bce_prob_fwd: workspace too small");
+  long long want = (n + 1023) / 1024;
+  const int grid = (int)(want < dd::kSMs * 4 ? want : dd::kSMs * 4);
+  bce_prob_kernel<<<grid, 256, 0, dd::as_stream(stream)>>>(probs, target, loss, (BceProbWs*)workspace, n);
+  return dd::check_launch("bce_prob_fwd");
+}
+
+extern "C" int dd_bce_prob_bwd(const float* probs, const float* target, const float* grad_out, float* dprobs, long long n,
+                               void* stream) {
+  DD_REQUIRE(probs && target && dprobs, DD_ERR_BAD_ARG, "dd_bce_prob_bwd: null pointer");
+  DD_REQUIRE(n > 0, DD_ERR_BAD_ARG, "dd_bce_prob_bwd: n=%lld", n);
+  bce_prob_bwd_kernel<<<grid_elems(n), 256, 0, dd::as_stream(stream)>>>(probs, target, grad_out, dprobs, n);
+  return dd::check_launch("bce_prob_bwd");
 }

@@ -112,7 +112,7 @@ class EncoderConvStack(torch.autograd.Function):
     (components.py:41-47).  ``inp`` is the views batch [B,6,3,H,W] (stitch folded into c1's loads)
     or a mosaic / NCHW image [B,3,H,Wm].  Activations are NHWC in ``act_dtype``.  Returns the
     pooled features [B, 8*H3*W3] (act_dtype) or, with ``c3_only``, the c3 activation as NCHW fp32
-    (components.py:44-45)."""
+    (components.py:44-45; ``c3_only == 2``: as the NHWC activation itself)."""
 
     @staticmethod
     def forward(ctx, inp, w1, b1, w2, b2, w3, b3, act_dtype, c3_only, impl):
@@ -136,7 +136,9 @@ class EncoderConvStack(torch.autograd.Function):
         a3 = torch.empty(B, H3, W3, 32, dtype=act_dtype, device=dev)
         call("dd_conv3x3_c32_fwd", a2.data_ptr(), w3.data_ptr(), b3.data_ptr(), a3.data_ptr(), code, B, H, Wm, 2,
              impl, st)
-        if c3_only:
+        if c3_only == 2:
+            out = a3               # the NHWC activation itself, for the bounding-box CNNs
+        elif c3_only:
             out = torch.empty(B, 32, H3, W3, dtype=torch.float32, device=dev)
             call("dd_nhwc_to_nchw_f32", a3.data_ptr(), code, out.data_ptr(), B, 32, H3, W3, st)
         else:
@@ -153,7 +155,10 @@ class EncoderConvStack(torch.autograd.Function):
         dev, st = g.device, stream_ptr()
         ws, ws_n = _conv_ws(dev)
         da3 = torch.empty_like(a3)
-        if c3_only:
+        if c3_only == 2:
+            g = _c(g.to(act_dtype))
+            call("dd_relu_mask", g.data_ptr(), a3.data_ptr(), da3.data_ptr(), code, da3.numel(), st)
+        elif c3_only:
             g = _c(g.float())
             call("dd_nchw_f32_to_nhwc", g.data_ptr(), da3.data_ptr(), code, B, 32, H3, W3, st)
             call("dd_relu_mask", da3.data_ptr(), a3.data_ptr(), da3.data_ptr(), code, da3.numel(), st)
@@ -183,7 +188,7 @@ class EncoderConvStack(torch.autograd.Function):
 
 def encoder_conv_stack(inp, c1, c2, c3, act_dtype=torch.float32, c3_only=False, impl=IMPL_AUTO):
     return EncoderConvStack.apply(inp, c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias, act_dtype,
-                                  bool(c3_only), int(impl))
+                                  int(c3_only), int(impl))
 
 
 # --------------------------------------------------------------------------------------------
@@ -445,10 +450,10 @@ def to_nchw(x):
 class Conv2dNHWC(torch.autograd.Function):
     """nn.Conv2d / nn.ConvTranspose2d (+ bias, + optional ReLU) on an NHWC activation [B,H,W,Cin] of
     fp32 or bf16; weight / bias fp32 in torch layout.  geom = (kernel, stride, padding, dilation,
-    transposed, output_padding), pairs like torch's."""
+    transposed, output_padding), pairs like torch's; act 0 none / 1 ReLU / 2 sigmoid."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, geom, relu):
+    def forward(ctx, x, weight, bias, geom, act):
         import ctypes
         _require_cuda(x, weight)
         k, s, p, d, transposed, opad = geom
@@ -465,9 +470,9 @@ class Conv2dNHWC(torch.autograd.Function):
         ws, n = _conv2d_ws(desc, x.device)
         bptr = _c(bias.detach().float()).data_ptr() if bias is not None else None
         call("dd_conv2d_fwd", x.data_ptr(), w.data_ptr(), bptr, y.data_ptr(), ctypes.byref(desc), dtype_code(x.dtype),
-             1 if relu else 0, ws.data_ptr(), n, stream_ptr())
-        ctx.desc, ctx.relu, ctx.has_bias = desc, relu, bias is not None
-        ctx.save_for_backward(x, w, y if relu else None)
+             int(act), ws.data_ptr(), n, stream_ptr())
+        ctx.desc, ctx.act, ctx.has_bias = desc, int(act), bias is not None
+        ctx.save_for_backward(x, w, y if act else None)
         return y
 
     @staticmethod
@@ -476,9 +481,10 @@ class Conv2dNHWC(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         desc, st, code = ctx.desc, stream_ptr(), dtype_code(x.dtype)
         dy = _c(dy.to(x.dtype))
-        if ctx.relu:
+        if ctx.act:
             dym = torch.empty_like(dy)
-            call("dd_relu_mask", dy.data_ptr(), y.data_ptr(), dym.data_ptr(), code, dy.numel(), st)
+            call("dd_relu_mask" if ctx.act == 1 else "dd_sigmoid_bwd", dy.data_ptr(), y.data_ptr(), dym.data_ptr(), code,
+                 dy.numel(), st)
             dy = dym
         ws, n = _conv2d_ws(desc, x.device)
         dx = dw = db = None
@@ -494,14 +500,18 @@ class Conv2dNHWC(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
-def conv2d_nhwc(x, module, relu=False):
-    """Apply an nn.Conv2d / nn.ConvTranspose2d parameter container to an NHWC activation."""
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+
+def conv2d_nhwc(x, module, relu=False, act=None):
+    """Apply an nn.Conv2d / nn.ConvTranspose2d parameter container to an NHWC activation
+    (act: ACT_NONE / ACT_RELU / ACT_SIGMOID fused after the bias; ``relu=True`` = ACT_RELU)."""
     transposed = isinstance(module, torch.nn.ConvTranspose2d)
     geom = (_pair(module.kernel_size), _pair(module.stride), _pair(module.padding), _pair(module.dilation), transposed,
             _pair(module.output_padding) if transposed else (0, 0))
     if module.groups != 1:
         raise RuntimeError("conv2d_nhwc: grouped convolutions are not part of the scene pipeline")
-    return Conv2dNHWC.apply(x, module.weight, module.bias, geom, bool(relu))
+    return Conv2dNHWC.apply(x, module.weight, module.bias, geom, int(act) if act is not None else int(bool(relu)))
 
 
 def decoder_deconv_stack(x, dc1, dc2, dc3, dc4, act_dtype=torch.float32):
@@ -513,3 +523,84 @@ def decoder_deconv_stack(x, dc1, dc2, dc3, dc4, act_dtype=torch.float32):
     a = conv2d_nhwc(a, dc3, relu=True)
     a = conv2d_nhwc(a, dc4, relu=False)
     return to_nchw(a)
+
+
+# --------------------------------------------------------------------------------------------
+# bounding-box model plumbing: camera extraction, tiling / concatenation, prob-space BCE
+# --------------------------------------------------------------------------------------------
+def view_extract(views, view: int, mode: int, dtype=torch.float32):
+    """One camera of every scene as an NHWC image with SpatialMappingCNN's rot90 / flip folded in
+    (spatial_bb/components.py:34-62).  mode 0 as is, 1 rot90(1,[2,3]), 2 rot90(1,[3,2]), 3 flip([2,3])."""
+    views = as_view_batch(views)
+    B, _, _, H, W = views.shape
+    Ho, Wo = (W, H) if mode in (1, 2) else (H, W)
+    out = torch.empty(B, Ho, Wo, 3, dtype=dtype, device=views.device)
+    call("dd_view_extract", views.data_ptr(), out.data_ptr(), dtype_code(dtype), B, H, W, int(view), int(mode), stream_ptr())
+    return out
+
+
+class TileNHWC(torch.autograd.Function):
+    """torch.cat of NHWC blocks into one tensor [B,H,W,C]: ``offsets[i] = (oy, ox, oc)`` of block i.
+    Backward hands every block its window of the gradient."""
+
+    @staticmethod
+    def forward(ctx, shape, offsets, *blocks):
+        B, H, W, Cn = shape
+        first = blocks[0]
+        out = torch.empty(B, H, W, Cn, dtype=first.dtype, device=first.device)
+        st, code = stream_ptr(), dtype_code(first.dtype)
+        ctx.meta = (shape, offsets, [tuple(b.shape) for b in blocks], first.dtype)
+        for blk, (oy, ox, oc) in zip(blocks, offsets):
+            blk = _c(blk)
+            _, h, w, c = blk.shape
+            call("dd_nhwc_place", blk.data_ptr(), out.data_ptr(), code, B, h, w, c, H, W, Cn, oy, ox, oc, 0, st)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (B, H, W, Cn), offsets, shapes, dtype = ctx.meta
+        g = _c(g.to(dtype))
+        st, code = stream_ptr(), dtype_code(dtype)
+        grads = []
+        for (oy, ox, oc), shp in zip(offsets, shapes):
+            d = torch.empty(shp, dtype=dtype, device=g.device)
+            call("dd_nhwc_place", d.data_ptr(), g.data_ptr(), code, B, shp[1], shp[2], shp[3], H, W, Cn, oy, ox, oc, 1, st)
+            grads.append(d)
+        return (None, None, *grads)
+
+
+def tile_nhwc(shape, offsets, blocks):
+    return TileNHWC.apply(tuple(shape), tuple(offsets), *blocks)
+
+
+def _bce_prob_ws(device):
+    n = int(_lib.load().dd_bce_prob_workspace_bytes())
+    return _ws.get("bce_prob", n, device, zero=True), n
+
+
+class BceProb(torch.autograd.Function):
+    """F.binary_cross_entropy(pred, target) on probabilities, mean (spatial_w_rm.py:131)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        _require_cuda(pred, target)
+        pred, target = _c(pred.float()), _c(target.float())
+        if pred.numel() != target.numel():
+            raise RuntimeError("bce_prob: prediction and target differ in size")
+        out = torch.empty(1, dtype=torch.float32, device=pred.device)
+        ws, n = _bce_prob_ws(pred.device)
+        call("dd_bce_prob_fwd", pred.data_ptr(), target.data_ptr(), out.data_ptr(), ws.data_ptr(), n, pred.numel(), stream_ptr())
+        ctx.save_for_backward(pred, target)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        d = torch.empty_like(pred)
+        gg = _c(g.float().reshape(1))
+        call("dd_bce_prob_bwd", pred.data_ptr(), target.data_ptr(), gg.data_ptr(), d.data_ptr(), pred.numel(), stream_ptr())
+        return d, None
+
+
+def bce_prob(pred, target):
+    return BceProb.apply(pred, target)

@@ -152,6 +152,26 @@ int dd_conv2d_wgrad(const void* x, const void* dy, float* dw, float* db, const d
                     int dtype, void* workspace, size_t ws_bytes, void* stream);
 size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d);
 
+/* ---- A15-A17: data movement and loss of the bounding-box model ------------------------------------
+ * dd_view_extract: one camera of every scene as an NHWC image [B,H',W',3] with the rot90 / flip of
+ * SpatialMappingCNN.forward (spatial_bb/components.py:34-62) folded into the indexing.
+ *   mode 0 as is; 1 rot90(k=1,[2,3]); 2 rot90(k=1,[3,2]); 3 flip([2,3]).  views fp32 [B,6,3,H,W].
+ * dd_nhwc_place: dir 0 copies small [B,h,w,c] into the window (oy,ox,oc) of big [B,H,W,C] (the
+ *   torch.cat calls at components.py:66-73,156); dir 1 copies the window back out (their backward).
+ * dd_sigmoid_bwd: out = dy * (1 - y) * y.
+ * dd_bce_prob_*: F.binary_cross_entropy on probabilities, mean, logs clamped at -100
+ *   (spatial_w_rm.py:131); bwd = g * (p - t) / max((1-p) p, 1e-12) / n. */
+int dd_view_extract(const float* views, void* out, int out_dtype, int B, int H, int W, int view, int mode,
+                    void* stream);
+int dd_nhwc_place(void* small_, void* big, int dtype, int B, int h, int w, int c, int H, int W, int C,
+                  int oy, int ox, int oc, int dir, void* stream);
+int dd_sigmoid_bwd(const void* dy, const void* y, void* out, int dtype, long long n, void* stream);
+int dd_bce_prob_fwd(const float* probs, const float* target, float* loss, void* workspace, size_t ws_bytes,
+                    long long n, void* stream);
+int dd_bce_prob_bwd(const float* probs, const float* target, const float* grad_out, float* dprobs,
+                    long long n, void* stream);
+size_t dd_bce_prob_workspace_bytes(void);
+
 /* ---- A14: mean squared error (autoencoder.py:91) ---------------------------------------------*/
 int dd_mse_fwd(const float* y, const float* y_hat, float* loss, void* workspace, size_t ws_bytes,
                long long n, void* stream);

@@ -163,6 +163,57 @@ def ae_case(name: str, batch: int, hidden: int, latent: int, view_h: int, view_w
     print(name, "slot", slot, "loss", float(gold.get("loss", float("nan"))))
 
 
+def bb_case(name: str, batch: int, hidden: int, latent: int):
+    """BBSpatialRoadMap (spatial_w_rm.py) at full geometry (the merging CNN only fits 256x306 views
+    and 800x800 maps).  The module imports boxes_to_binary_map from src.utils.helper, where it
+    does not exist: inject the real one from src.utils.bb_to_img before the import --
+    a test-time patch of the module namespace, no reference file is edited."""
+    import src.utils.helper as ref_helper
+    import src.utils.bb_to_img as ref_bb
+    ref_helper.boxes_to_binary_map = ref_bb.boxes_to_binary_map
+    from src.bounding_box_model.spatial_bb.spatial_w_rm import BBSpatialRoadMap
+
+    params = so.init_bb_params(hidden, latent)
+    ns = Namespace(hidden_dim=hidden, latent_dim=latent, input_width=6 * 306, input_height=256, output_width=306,
+                   output_height=256, in_channels=3, batch_size=batch, learning_rate=1e-3, output_img_freq=10 ** 9,
+                   link="/nonexistent")
+    ae = BasicAE(ns)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ae.ckpt")
+        torch.save({"state_dict": ae.state_dict(), "hparams": vars(ns)}, path)
+        del ae
+        torch.manual_seed(20200505)
+        model = BBSpatialRoadMap(Namespace(pretrained_path=path, learning_rate=1e-3, batch_size=batch,
+                                           output_img_freq=10 ** 9, unfreeze_epoch_no=0, link="/nonexistent",
+                                           mse_loss=False))
+    sd = model.state_dict()
+    assert all(k in sd and sd[k].shape == v.shape for k, v in params.items())
+    missing = model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=False)
+    assert not missing.unexpected_keys
+    views, road = so.synthetic_scene_batch(batch, 256, 306, seed=20200508)
+    boxes = so.synthetic_boxes(batch)
+    target = tuple({"bounding_box": b} for b in boxes)
+    model.logger = None
+    model.frozen = False
+    model.ae.unfreeze()
+    model.train()
+    batch_t = (tuple(views.unbind(0)), target, tuple(road.unbind(0)))
+    loss, tgt, pred = model._run_step(batch_t, 1, "train")
+    loss.backward()
+    grads = {k: v.grad for k, v in model.named_parameters() if v.grad is not None}
+    # the oracle's restatement of the rasteriser and of the whole step
+    tgt_o = torch.from_numpy(np.stack([so.boxes_to_binary_map(b).copy() for b in boxes])).float()
+    assert torch.equal(tgt_o.reshape(batch, -1), tgt)
+    gold = dict(name=name, batch=batch, hidden=hidden, latent=latent, seed_x=20200508,
+                loss=loss.detach().clone(), pred_sample=sample(pred), pred_absmax=float(pred.abs().max()),
+                target_ones=int(tgt.sum()), target_sha=sha(tgt),
+                params_sha={k: sha(v) for k, v in params.items()},
+                grad_norm={k: float(v.double().norm()) for k, v in grads.items()},
+                grad_sample={k: sample(v, 512) for k, v in grads.items()})
+    torch.save(gold, os.path.join(GOLD, name + ".pt"))
+    print(name, "loss", float(loss), "target ones", gold["target_ones"], "grads", len(grads))
+
+
 def binarise_case():
     """Exhaustive fp32 sweep around 0 through the reference's own sigmoid().round() (:140)."""
     lo = np.float32(2.0 ** -27).view(np.uint32)
@@ -183,6 +234,9 @@ def binarise_case():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "bb":
+        bb_case("bb_full_b1", batch=1, hidden=8, latent=8)
+        sys.exit(0)
     binarise_case()
     roadmap_case("roadmap_small", batch=4, hidden=16, latent=8, view_h=16, view_w=20,
                  with_grads=True, store_params=True)

@@ -282,6 +282,133 @@ def ae_run_step(p: dict, views: torch.Tensor, target_slot: int, training: bool, 
     return dict(loss=F.mse_loss(y, y_hat), x=x, y=y, z=z, y_hat=y_hat)
 
 
+# ----------------------------------------------------------------------------------------
+# A15-A17: bounding-box model with roadmap input (config 4)
+# ----------------------------------------------------------------------------------------
+def view_transform(views: torch.Tensor, view: int, mode: int) -> torch.Tensor:
+    """One camera of the batch as an image [B,3,H',W'], restated as explicit index maps (numpy):
+    mode 0: as is; 1: torch.rot90(x, 1, [2,3]) -> out[i,j] = x[j, W-1-i]; 2: torch.rot90(x, 1, [3,2])
+    -> out[i,j] = x[H-1-j, i]; 3: torch.flip(x, [2,3]) -> out[i,j] = x[H-1-i, W-1-j]
+    (spatial_bb/components.py:34-62)."""
+    v = views[:, view].detach().cpu().numpy()
+    if mode == 0:
+        out = v
+    elif mode == 1:
+        out = np.transpose(v, (0, 1, 3, 2))[:, :, ::-1, :]
+    elif mode == 2:
+        out = np.transpose(v, (0, 1, 3, 2))[:, :, :, ::-1]
+    else:
+        out = v[:, :, ::-1, ::-1]
+    return torch.from_numpy(np.ascontiguousarray(out))
+
+
+# (name, camera index, transform mode) in the order the strips are computed; canvas cell (row, col)
+BB_STRIPS = (("bl_conv", 3, 0, (0, 0)), ("fl_conv", 0, 0, (0, 1)), ("b_conv", 4, 1, (1, 0)), ("f_conv", 1, 2, (1, 1)),
+             ("br_conv", 5, 3, (2, 0)), ("fr_conv", 2, 3, (2, 1)))
+
+
+def spatial_mapping_forward(p: dict, views: torch.Tensor, prefix: str = "space_map_cnn.") -> torch.Tensor:
+    """spatial_bb/components.py:28-77 (SpatialMappingCNN.forward): six strip convs (+ReLU) on the
+    plain / rotated / flipped cameras, tiled 3 x 2 into a square canvas, 3x3 valid conv + ReLU."""
+    cells = {}
+    for name, cam, mode, cell in BB_STRIPS:
+        img = view_transform(views, cam, mode)
+        pad = 1 if name in ("f_conv", "b_conv") else 0          # :18,22 (padding=(1))
+        cells[cell] = F.relu(F.conv2d(img, p[prefix + name + ".weight"], p[prefix + name + ".bias"], stride=(3, 2),
+                                      padding=pad))
+    rows = [torch.cat([cells[(r, 0)], cells[(r, 1)]], dim=3) for r in range(3)]
+    canvas = torch.cat(rows, dim=2)
+    return F.relu(F.conv2d(canvas, p[prefix + "out_conv.weight"], p[prefix + "out_conv.bias"]))
+
+
+def merging_forward(p: dict, ssr, spatial_map, rm, prefix: str = "box_merge.") -> torch.Tensor:
+    """spatial_bb/components.py:141-170 (RoadMapBoxesMergingCNN.forward) -> probabilities [B,1,800,800]."""
+    w = lambda n: p[prefix + n + ".weight"]  # noqa: E731
+    b = lambda n: p[prefix + n + ".bias"]    # noqa: E731
+    ssr = F.relu(F.conv2d(ssr, w("ss_conv"), b("ss_conv"), stride=(1, 7)))
+    ssr = F.relu(F.conv_transpose2d(ssr, w("ss_deconv"), b("ss_deconv"), stride=2))
+    rm = F.relu(F.conv2d(rm, w("rm_conv_1"), b("rm_conv_1"), stride=3, dilation=3, padding=1))
+    rm = F.relu(F.conv2d(rm, w("rm_conv_2"), b("rm_conv_2"), dilation=3))
+    x = torch.cat([ssr, spatial_map, rm], dim=1)
+    x = F.relu(F.conv_transpose2d(x, w("up_conv_1"), b("up_conv_1"), dilation=7))
+    x = F.relu(F.conv_transpose2d(x, w("up_conv_2"), b("up_conv_2"), dilation=7))
+    x = F.relu(F.conv_transpose2d(x, w("up_conv_3"), b("up_conv_3"), dilation=7))
+    x = F.relu(F.conv_transpose2d(x, w("up_conv_4"), b("up_conv_4"), dilation=3))
+    return torch.sigmoid(F.conv_transpose2d(x, w("up_conv_5"), b("up_conv_5"), stride=2))
+
+
+def bb_forward(p: dict, views: torch.Tensor, rm: torch.Tensor) -> torch.Tensor:
+    """spatial_w_rm.py:67-83 (BBSpatialRoadMap.forward): views [B,6,3,H,W], rm [B,1,800,800] -> [B,800,800]."""
+    space_rep = spatial_mapping_forward(p, views)
+    _, _, ssr = encoder_convs(p, stitch(views))            # encoder with c3_only (spatial_w_rm.py:47)
+    return merging_forward(p, ssr, space_rep, rm).squeeze(1)
+
+
+def bb_run_step(p: dict, views, road_image, target_bb_img, mse_loss: bool = False):
+    """spatial_w_rm.py:97-133 with the rasterised box target passed in (bb_to_img.py is host-side
+    label preparation): prob-space BCE (torch clamps each log at -100) or MSE."""
+    rm = road_image.float().unsqueeze(1)
+    pred = bb_forward(p, views, rm)
+    b = pred.shape[0]
+    pv, tv = pred.reshape(b, -1), target_bb_img.float().reshape(b, -1)
+    loss = F.mse_loss(pv, tv) if mse_loss else F.binary_cross_entropy(pv, tv)
+    return dict(loss=loss, pred=pred)
+
+
+def boxes_to_binary_map(boxes: torch.Tensor) -> np.ndarray:
+    """utils/bb_to_img.py:5-21 restated: boxes [N,2,4] (metres; rows x/y; cols fl, fr, bl, br) ->
+    800x800 map; polygon corner order fl, fr, br, bl; pixel = metre*10 + 400; vertical flip."""
+    from PIL import Image, ImageDraw
+    x = boxes.cpu().numpy()
+    img = Image.fromarray(np.zeros((800, 800)))
+    draw = ImageDraw.Draw(img)
+    for i in range(x.shape[0]):
+        box = np.stack([x[i][:, 0], x[i][:, 1], x[i][:, 3], x[i][:, 2]]) * 10 + 400
+        draw.polygon(list(box.flatten()), fill=1)
+    return np.flip(np.asarray(img), 0)
+
+
+def synthetic_boxes(batch: int, seed: int = 20200507):
+    """5-20 axis-aligned 4.6 m x 2 m boxes per scene, centres U(-30, 30) m."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(batch):
+        n = int(torch.randint(5, 21, (1,), generator=g))
+        c = torch.rand(n, 2, generator=g) * 60 - 30
+        dx, dy = 2.3, 1.0
+        xs = torch.stack([c[:, 0] + dx, c[:, 0] + dx, c[:, 0] - dx, c[:, 0] - dx], dim=1)
+        ys = torch.stack([c[:, 1] + dy, c[:, 1] - dy, c[:, 1] + dy, c[:, 1] - dy], dim=1)
+        out.append(torch.stack([xs, ys], dim=1))
+    return out
+
+
+def init_bb_params(hidden: int, latent: int, view_h: int = 256, view_w: int = 306, seed: int = 20200505) -> dict:
+    """Random-init BBSpatialRoadMap parameters keyed like its state_dict: the AE encoder (through
+    init_roadmap_params' generator, prefix ae.encoder.), then SpatialMappingCNN and
+    RoadMapBoxesMergingCNN layers built by torch's own constructors (default init) in the
+    reference's order (spatial_bb/components.py:16-26,127-139) under torch.manual_seed(seed)."""
+    from torch import nn
+    p = {k: v for k, v in init_roadmap_params(hidden, latent, view_h, view_w, map_hw=8, seed=seed).items()
+         if k.startswith("ae.encoder.")}
+    state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    space = [("f_conv", nn.Conv2d(3, 32, (52, 1), (3, 2), 1)), ("fl_conv", nn.Conv2d(3, 32, (1, 50), (3, 2))),
+             ("fr_conv", nn.Conv2d(3, 32, (1, 50), (3, 2))), ("b_conv", nn.Conv2d(3, 32, (52, 1), (3, 2), 1)),
+             ("bl_conv", nn.Conv2d(3, 32, (1, 50), (3, 2))), ("br_conv", nn.Conv2d(3, 32, (1, 50), (3, 2))),
+             ("out_conv", nn.Conv2d(32, 32, 3))]
+    merge = [("ss_conv", nn.Conv2d(32, 32, (1, 24), (1, 7))), ("ss_deconv", nn.ConvTranspose2d(32, 32, 2, 2)),
+             ("rm_conv_1", nn.Conv2d(1, 32, 7, 3, 1, 3)), ("rm_conv_2", nn.Conv2d(32, 32, 3, 1, 0, 3)),
+             ("up_conv_1", nn.ConvTranspose2d(96, 64, 7, 1, dilation=7)), ("up_conv_2", nn.ConvTranspose2d(64, 32, 7, 1, dilation=7)),
+             ("up_conv_3", nn.ConvTranspose2d(32, 16, 7, 1, dilation=7)), ("up_conv_4", nn.ConvTranspose2d(16, 8, 7, 1, dilation=3)),
+             ("up_conv_5", nn.ConvTranspose2d(8, 1, 2, 2))]
+    torch.random.set_rng_state(state)
+    for prefix, layers in (("space_map_cnn.", space), ("box_merge.", merge)):
+        for name, m in layers:
+            p[prefix + name + ".weight"] = m.weight.detach().clone()
+            p[prefix + name + ".bias"] = m.bias.detach().clone()
+    return p
+
+
 def strided_sample(t: torch.Tensor, n: int = 4096) -> torch.Tensor:
     """n evenly spaced elements of the flattened tensor (integer index arithmetic); how the
     golden files keep a checkable slice of tensors too large to commit."""

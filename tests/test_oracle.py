@@ -119,3 +119,30 @@ def test_full_size_eval(golden):
     assert torch.equal(out["loss"], e["loss"])
     assert torch.equal(out["ts_rounded"], e["ts_rounded"])
     assert sha(so.binarise(out["logits"], from_logits=True).to(torch.uint8)) == e["binary_sha"]
+
+
+def _bb_inputs(g):
+    import numpy as np
+    p = so.init_bb_params(g["hidden"], g["latent"])
+    views, road = so.synthetic_scene_batch(g["batch"], 256, 306, seed=g["seed_x"])
+    boxes = so.synthetic_boxes(g["batch"])
+    target = torch.from_numpy(np.stack([so.boxes_to_binary_map(b).copy() for b in boxes])).float()
+    return p, views, road, target
+
+
+@pytest.mark.slow
+def test_bb_full_b1(golden):
+    """Bounding-box model with roadmap input (config 4), full geometry, B=1: the oracle's restatement
+    against the unmodified reference's _run_step (loss, prediction sample, every gradient)."""
+    g = golden("bb_full_b1")
+    p, views, road, target = _bb_inputs(g)
+    for k, v in p.items():
+        assert sha(v) == g["params_sha"][k], k
+    assert int(target.sum()) == g["target_ones"] and sha(target.reshape(g["batch"], -1)) == g["target_sha"]
+    q = {k: v.clone().requires_grad_(k in g["grad_norm"]) for k, v in p.items()}
+    out = so.bb_run_step(q, views, road, target)
+    assert torch.equal(out["loss"].detach(), g["loss"])
+    assert torch.equal(so.strided_sample(out["pred"]), g["pred_sample"])
+    out["loss"].backward()
+    for k in g["grad_norm"]:
+        assert torch.equal(so.strided_sample(q[k].grad, 512), g["grad_sample"][k]), k
