@@ -38,9 +38,10 @@ class DenseBlock(nn.Module):
         self.fc_bn = nn.BatchNorm1d(out_dim)
         self.in_dim = in_dim
         self.impl = IMPL_AUTO
+        self.allow_tf32 = False       # set by the owner on the bf16 (reduced-precision) path
 
     def forward(self, x):
-        x = ops.linear(x, self.fc1.weight, self.fc1.bias, self.impl)
+        x = ops.linear(x, self.fc1.weight, self.fc1.bias, self.impl, allow_tf32=self.allow_tf32)
         x = self.fc_bn(x)
         x = F.relu(x)
         return F.dropout(x, self.drop_p)
@@ -115,6 +116,7 @@ class Decoder(nn.Module):
         self.latent_dim = latent_dim
         self.fc1 = DenseBlock(latent_dim, hidden_dim)
         self.fc2 = DenseBlock(hidden_dim, self.deconv_dim_h * self.deconv_dim_w * 64)
+        self.fc2.allow_tf32 = self.compute_dtype == torch.bfloat16
         self.dc1 = nn.ConvTranspose2d(64, 32, kernel_size=3, padding=1)
         self.dc2 = nn.ConvTranspose2d(32, 32, kernel_size=3, padding=1)
         self.dc3 = nn.ConvTranspose2d(32, 32, kernel_size=2, stride=2)

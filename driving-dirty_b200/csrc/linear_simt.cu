@@ -371,16 +371,26 @@ size_t ws_bytes_for(int B, int N, long long K) {
 }  // namespace
 
 namespace dd {
-// tensor-core weight-streaming variants (linear_tc.cu); return DD_ERR_UNSUPPORTED when a shape
-// is outside what they implement so that DD_IMPL_AUTO can fall through to the SIMT kernels.
-int linear_fwd_tc(const void* x, int x_dtype, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes,
-                  int B, int N, long long K, cudaStream_t st);
-bool linear_tc_supported(int pass, int B, int N, long long K);
+// tensor-core weight-streaming variants (linear_tc.cu): fp32 operands read as tf32, B <= 32 rows per call
+bool linear_tc_supported(int B, int N, long long K);
+size_t linear_tc_workspace_bytes(int B, int N, long long K);
+int linear_fwd_tc(const float* x, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes, int B, int N,
+                  long long K, cudaStream_t st);
+int linear_dgrad_tc(const float* dy, const float* w, void* dx, int dx_dtype, void* ws, size_t ws_bytes, int B, int N,
+                    long long K, cudaStream_t st);
+int linear_wgrad_tc(const float* dy, const float* x, float* dw, int B, int N, long long K, int accumulate, cudaStream_t st);
 }  // namespace dd
+
+// tcgen05 path: only on explicit request (DD_IMPL_TCGEN05) -- fp32 callers under DD_IMPL_AUTO keep the
+// 1e-5 parity kernels; tf32 operands are the bf16-mode contract (1e-2)
+static bool use_tc(int impl, int B, int N, long long K) { return impl == DD_IMPL_TCGEN05 && dd::linear_tc_supported(B, N, K); }
+
+extern "C" int dd_linear_tc_supported(int B, int N, long long K) { return dd::linear_tc_supported(B, N, K) ? 1 : 0; }
 
 extern "C" size_t dd_linear_workspace_bytes(int B, int N, long long K) {
   if (B <= 0 || N <= 0 || K <= 0) return 256;
-  return ws_bytes_for(B, N, K);
+  const size_t a = ws_bytes_for(B, N, K), b = dd::linear_tc_supported(B, N, K) ? dd::linear_tc_workspace_bytes(B, N, K) : 0;
+  return a > b ? a : b;
 }
 
 #define DD_LINEAR_COMMON(name)                                                                           \
@@ -394,9 +404,10 @@ extern "C" int dd_linear_fwd(const void* x, int x_dtype, const float* w, const f
   DD_LINEAR_COMMON("dd_linear_fwd");
   DD_REQUIRE(x_dtype == DD_F32 || x_dtype == DD_BF16, DD_ERR_UNSUPPORTED, "dd_linear_fwd: dtype %d", x_dtype);
   DD_REQUIRE((uintptr_t)w % 16 == 0, DD_ERR_ALIGNMENT, "dd_linear_fwd: weight pointer must be 16-byte aligned");
-  DD_REQUIRE(workspace && ws_bytes >= ws_bytes_for(B, N, K), DD_ERR_WORKSPACE, "dd_linear_fwd: workspace %zu < %zu",
-             ws_bytes, ws_bytes_for(B, N, K));
-  DD_REQUIRE(impl != DD_IMPL_TCGEN05, DD_ERR_UNSUPPORTED, "dd_linear_fwd: tcgen05 path not built yet");
+  DD_REQUIRE(workspace && ws_bytes >= dd_linear_workspace_bytes(B, N, K), DD_ERR_WORKSPACE,
+             "dd_linear_fwd: workspace %zu < %zu", ws_bytes, dd_linear_workspace_bytes(B, N, K));
+  DD_REQUIRE(impl != DD_IMPL_TCGEN05 || (x_dtype == DD_F32 && dd::linear_tc_supported(B, N, K)), DD_ERR_UNSUPPORTED,
+             "dd_linear_fwd: tcgen05 path needs fp32 x, N %% 4 == K %% 4 == 0 and N*K >= 2^22 (B=%d N=%d K=%lld)", B, N, K);
   cudaStream_t st = dd::as_stream(stream);
   const size_t esz = x_dtype == DD_F32 ? 4 : 2;
   for (int b0 = 0; b0 < B; b0 += 32) {
@@ -404,6 +415,10 @@ extern "C" int dd_linear_fwd(const void* x, int x_dtype, const float* w, const f
     const char* xp = (const char*)x + (size_t)b0 * K * esz;
     float* yp = y + (size_t)b0 * N;
     int e;
+    if (use_tc(impl, B, N, K)) {
+      if ((e = dd::linear_fwd_tc((const float*)xp, w, bias, yp, workspace, ws_bytes, bc, N, K, st))) return e;
+      continue;
+    }
     if (x_dtype == DD_F32)
       e = bc <= 8 ? fwd_launch<float, 8>((const float*)xp, w, bias, yp, (float*)workspace, bc, N, K, st)
                   : fwd_launch<float, 32>((const float*)xp, w, bias, yp, (float*)workspace, bc, N, K, st);
@@ -421,9 +436,10 @@ extern "C" int dd_linear_dgrad(const float* dy, const float* w, void* dx, int dx
   DD_LINEAR_COMMON("dd_linear_dgrad");
   DD_REQUIRE(dx_dtype == DD_F32 || dx_dtype == DD_BF16, DD_ERR_UNSUPPORTED, "dd_linear_dgrad: dtype %d", dx_dtype);
   DD_REQUIRE((uintptr_t)w % 16 == 0, DD_ERR_ALIGNMENT, "dd_linear_dgrad: weight pointer must be 16-byte aligned");
-  DD_REQUIRE(workspace && ws_bytes >= ws_bytes_for(B, N, K), DD_ERR_WORKSPACE, "dd_linear_dgrad: workspace %zu < %zu",
-             ws_bytes, ws_bytes_for(B, N, K));
-  DD_REQUIRE(impl != DD_IMPL_TCGEN05, DD_ERR_UNSUPPORTED, "dd_linear_dgrad: tcgen05 path not built yet");
+  DD_REQUIRE(workspace && ws_bytes >= dd_linear_workspace_bytes(B, N, K), DD_ERR_WORKSPACE,
+             "dd_linear_dgrad: workspace %zu < %zu", ws_bytes, dd_linear_workspace_bytes(B, N, K));
+  DD_REQUIRE(impl != DD_IMPL_TCGEN05 || dd::linear_tc_supported(B, N, K), DD_ERR_UNSUPPORTED,
+             "dd_linear_dgrad: tcgen05 path needs N %% 4 == K %% 4 == 0 and N*K >= 2^22 (B=%d N=%d K=%lld)", B, N, K);
   cudaStream_t st = dd::as_stream(stream);
   const size_t esz = dx_dtype == DD_F32 ? 4 : 2;
   for (int b0 = 0; b0 < B; b0 += 32) {
@@ -431,6 +447,10 @@ extern "C" int dd_linear_dgrad(const float* dy, const float* w, void* dx, int dx
     const float* dyp = dy + (size_t)b0 * N;
     char* dxp = (char*)dx + (size_t)b0 * K * esz;
     int e;
+    if (use_tc(impl, B, N, K)) {
+      if ((e = dd::linear_dgrad_tc(dyp, w, dxp, dx_dtype, workspace, ws_bytes, bc, N, K, st))) return e;
+      continue;
+    }
     if (dx_dtype == DD_F32)
       e = bc <= 8 ? dgrad_launch<float, 8>(dyp, w, (float*)dxp, (float*)workspace, bc, N, K, st)
                   : dgrad_launch<float, 32>(dyp, w, (float*)dxp, (float*)workspace, bc, N, K, st);
@@ -449,7 +469,8 @@ extern "C" int dd_linear_wgrad(const float* dy, const void* x, int x_dtype, floa
   DD_REQUIRE(K % 4 == 0, DD_ERR_UNSUPPORTED, "dd_linear_wgrad: K=%lld must be a multiple of 4", K);
   DD_REQUIRE(x_dtype == DD_F32 || x_dtype == DD_BF16, DD_ERR_UNSUPPORTED, "dd_linear_wgrad: dtype %d", x_dtype);
   DD_REQUIRE((uintptr_t)dw % 16 == 0, DD_ERR_ALIGNMENT, "dd_linear_wgrad: dw pointer must be 16-byte aligned");
-  DD_REQUIRE(impl != DD_IMPL_TCGEN05, DD_ERR_UNSUPPORTED, "dd_linear_wgrad: tcgen05 path not built yet");
+  DD_REQUIRE(impl != DD_IMPL_TCGEN05 || (x_dtype == DD_F32 && dd::linear_tc_supported(B, N, K)), DD_ERR_UNSUPPORTED,
+             "dd_linear_wgrad: tcgen05 path needs fp32 x, N %% 4 == K %% 4 == 0 and N*K >= 2^22 (B=%d N=%d K=%lld)", B, N, K);
   cudaStream_t st = dd::as_stream(stream);
   const size_t esz = x_dtype == DD_F32 ? 4 : 2;
   for (int b0 = 0; b0 < B; b0 += 32) {
@@ -458,7 +479,8 @@ extern "C" int dd_linear_wgrad(const float* dy, const void* x, int x_dtype, floa
     const char* xp = (const char*)x + (size_t)b0 * K * esz;
     const int accumulate = b0 > 0;
     int e;
-    if (x_dtype == DD_F32)
+    if (use_tc(impl, B, N, K)) e = dd::linear_wgrad_tc(dyp, (const float*)xp, dw, bc, N, K, accumulate, st);
+    else if (x_dtype == DD_F32)
       e = bc <= 8 ? wgrad_launch<float, 8>(dyp, (const float*)xp, dw, bc, N, K, accumulate, st)
                   : wgrad_launch<float, 32>(dyp, (const float*)xp, dw, bc, N, K, accumulate, st);
     else

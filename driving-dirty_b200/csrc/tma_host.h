@@ -1,0 +1,60 @@
+// Host-side TMA descriptor (CUtensorMap) construction without linking libcuda: the driver entry point
+// cuTensorMapEncodeTiled is fetched through the runtime (cudaGetDriverEntryPoint).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace dd {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Row-major 2-D matrix [rows][cols] of 4-byte (fp32) or 2-byte (bf16) elements, row pitch in elements;
+// box = box_cols x box_rows, 128-byte swizzle (box_cols * elem_bytes must be 128; atom32: the 32-byte-atom
+// variant that MN-major tf32 operands need), out-of-range = 0.
+// Returns 0 on success.
+inline int tma_map_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                      uint32_t box_cols, uint32_t box_rows, bool atom32 = false) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc) return -1;
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on the calling thread.  PyTorch's
+  // autograd worker threads may not have one yet (the runtime binds it lazily; seen as error 201 =
+  // CUDA_ERROR_INVALID_CONTEXT from backward passes) -- a runtime no-op binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch_elems * (uint64_t)elem_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// last failing encode, for error texts
+inline int tma_map_2d_checked(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                              uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows, bool atom32, char* msg, size_t msg_len) {
+  const int r = tma_map_2d(map, base, elem_bytes, rows, cols, pitch_elems, box_cols, box_rows, atom32);
+  if (r != 0 && msg)
+    snprintf(msg, msg_len, "cuTensorMapEncodeTiled -> %d (base %p, rows %llu, cols %llu, pitch %llu, box %ux%u, atom32 %d)", r, base,
+             (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_elems, box_cols, box_rows, (int)atom32);
+  return r;
+}
+
+}  // namespace dd

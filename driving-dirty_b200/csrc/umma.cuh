@@ -183,3 +183,51 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 }  // namespace umma
+
+// ---------------------------------------------------------------- 128B-swizzled operands / TMA ----
+namespace umma {
+
+// shared-memory matrix descriptor, SWIZZLE_128B (what a TMA box with a 128-byte inner extent and
+// CU_TENSOR_MAP_SWIZZLE_128B produces; tile base 1024-byte aligned):
+//   K-major : rows of 128 B (one swizzle span of K), 8-row atoms of 1024 B; SBO = stride between 8-row
+//             groups along M/N; LBO unused; advancing K inside the span = start address + bytes
+//   MN-major: rows = K index, 128 B = 32 fp32 (64 bf16) MN elements; LBO = stride between MN blocks,
+//             SBO = stride between groups of 8 K rows
+__device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);   // version 1, layout_type 2 = SWIZZLE_128B (bits 61-63)
+}
+// SWIZZLE_128B_BASE32B (layout_type 1): the only layout for MN-major tf32 operands; 4-row K atoms
+// (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); SBO = stride between groups of 4 K rows
+__device__ __forceinline__ uint32_t desc_hi_sw128_base32(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (1u << 29);
+}
+
+// kind::tf32 instruction descriptor: tf32 x tf32 -> fp32 (operands are fp32 words in shared memory)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// TMA: 2-D tile global -> shared, completion counted in bytes on an mbarrier.  c0 = innermost coordinate.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+}  // namespace umma

@@ -201,7 +201,9 @@ def _linear_ws(B, N, K, device):
 
 class SkinnyLinear(torch.autograd.Function):
     """y = x W^T + b for a small batch and a very wide K or N (nn.Linear at components.py:105,
-    roadmap_bce_v2.py:75).  x: [B,K] fp32 or bf16; W [N,K], b [N], y [B,N] fp32."""
+    roadmap_bce_v2.py:75).  x: [B,K] fp32 or bf16; W [N,K], b [N], y [B,N] fp32.
+    ``impl``: IMPL_SIMT = fp32 CUDA-core kernels (1e-5 parity); IMPL_TCGEN05 = TMA + tcgen05 tf32
+    weight-streaming kernels (x is read as fp32)."""
 
     @staticmethod
     def forward(ctx, x, w, b, impl):
@@ -211,6 +213,9 @@ class SkinnyLinear(torch.autograd.Function):
             wd = wd.float()
         B, K = x.shape
         N = wd.shape[0]
+        ctx.x_dtype = x.dtype
+        if impl == _lib.IMPL_TCGEN05 and x.dtype != torch.float32:
+            x = x.float()          # the tf32 path streams fp32 operands through TMA
         y = torch.empty(B, N, dtype=torch.float32, device=x.device)
         ws, n = _linear_ws(B, N, K, x.device)
         bias_ptr = _c(b.detach().float()).data_ptr() if b is not None else None
@@ -230,9 +235,9 @@ class SkinnyLinear(torch.autograd.Function):
         st = stream_ptr()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
+            dx = torch.empty(B, K, dtype=ctx.x_dtype, device=x.device)
             ws, n = _linear_ws(B, N, K, x.device)
-            call("dd_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), dtype_code(x.dtype), ws.data_ptr(), n,
+            call("dd_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), dtype_code(ctx.x_dtype), ws.data_ptr(), n,
                  B, N, K, ctx.impl, st)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
@@ -244,8 +249,16 @@ class SkinnyLinear(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def linear(x, weight, bias=None, impl=IMPL_AUTO):
-    return SkinnyLinear.apply(x, weight, bias, int(impl))
+def linear(x, weight, bias=None, impl=IMPL_AUTO, allow_tf32=False):
+    """IMPL_AUTO: the tensor-core (tf32) kernels when the caller is on the reduced-precision path
+    (bf16 activations, or ``allow_tf32``) and the layer is wide enough to stream; else fp32 CUDA cores."""
+    impl = int(impl)
+    if impl == IMPL_AUTO:
+        B, K = x.shape
+        fast = (x.dtype == torch.bfloat16 or allow_tf32) and x.is_cuda and \
+            bool(_lib.load().dd_linear_tc_supported(B, weight.shape[0], K))
+        impl = _lib.IMPL_TCGEN05 if fast else _lib.IMPL_SIMT
+    return SkinnyLinear.apply(x, weight, bias, impl)
 
 
 # --------------------------------------------------------------------------------------------

@@ -46,7 +46,8 @@ class RoadMapBCE(LightningModule):
 
     def _logits(self, x):
         z = self.ae.encoder.forward_views(x)          # stitch folded into the first conv
-        y = ops.linear(z, self.fc1.weight, self.fc1.bias, self.impl)
+        y = ops.linear(z, self.fc1.weight, self.fc1.bias, self.impl,
+                       allow_tf32=self.ae.encoder.compute_dtype == torch.bfloat16)
         return y.reshape(y.size(0), self.map_size, self.map_size)
 
     def forward(self, x):

@@ -110,6 +110,10 @@ int dd_linear_dgrad(const float* dy, const float* w, void* dx, int dx_dtype, voi
 int dd_linear_wgrad(const float* dy, const void* x, int x_dtype, float* dw, float* db, int B,
                     int N, long long K, int impl, void* stream);
 size_t dd_linear_workspace_bytes(int B, int N, long long K);
+/* impl = DD_IMPL_TCGEN05 runs the weight-streaming tensor-core kernels (fp32 operands read as tf32 through
+ * TMA; x must be fp32): allowed when this returns 1 (N, K multiples of 4, N*K >= 2^22).  DD_IMPL_AUTO
+ * keeps the fp32 CUDA-core kernels (1e-5 parity). */
+int dd_linear_tc_supported(int B, int N, long long K);
 
 /* ---- A8-A11: sigmoid + BCE-with-logits + threat scores + binarise -----------------------------
  * roadmap_bce_v2.py:81 (sigmoid), :106 (binary_cross_entropy_with_logits, mean), :140 (.round()),

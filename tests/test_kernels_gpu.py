@@ -302,6 +302,36 @@ def test_linear_fwd_dgrad_wgrad(dd, xdtype, tol, B, N, K):
     assert rel_max_err(bd.grad, b.grad) < tol
 
 
+TF32_TOL = 2e-3   # tf32 operands (10-bit mantissa) on the weight-streaming tensor-core path
+
+
+@pytest.mark.parametrize("xdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,K", [(32, 256, 16384 + 64), (5, 1028, 4100), (32, 66000, 128), (3, 640000, 8),
+                                    (32, 16, 300000), (40, 4096, 1024), (32, 256, 940032)])
+def test_linear_tcgen05_fwd_dgrad_wgrad(dd, xdtype, B, N, K):
+    """TMA-fed tcgen05 (tf32) weight-streaming kernels against torch's fp32 CPU linear and autograd."""
+    g = torch.Generator().manual_seed(61 + B)
+    x = q(torch.randn(B, K, generator=g), xdtype).requires_grad_(True)
+    w = ((torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5).requires_grad_(True)
+    b = ((torch.rand(N, generator=g) * 2 - 1) * 0.1).requires_grad_(True)
+    y = F.linear(x, w, b)
+    dy = torch.randn(B, N, generator=g)
+    y.backward(dy)
+    xd = x.detach().to(xdtype).cuda().requires_grad_(True)
+    wd = w.detach().cuda().requires_grad_(True)
+    bd = b.detach().cuda().requires_grad_(True)
+    yd = dd.linear(xd, wd, bd, impl=2)
+    assert rel_max_err(yd, y) < TF32_TOL
+    yd.backward(dy.cuda())
+    assert rel_max_err(xd.grad, x.grad) < (TF32_TOL if xdtype == torch.float32 else BF16_TOL)
+    assert rel_max_err(wd.grad, w.grad) < TF32_TOL
+    assert rel_max_err(bd.grad, b.grad) < FP32_TOL
+    # deterministic: the split reductions are ordered
+    xd2 = x.detach().to(xdtype).cuda().requires_grad_(True)
+    yd2 = dd.linear(xd2, wd, bd, impl=2)
+    assert torch.equal(yd2, yd)
+
+
 # ------------------------------------------------------------------------------- loss / TS ---
 def _ref_loss_bundle(logits, target):
     probs = torch.sigmoid(logits)
