@@ -286,6 +286,346 @@ int launch(const void* in, const float* w, const float* bias, const void* mask, 
 
 
 // ================================================================================================
+// Stride-1 32->32 3x3 conv (c2 forward, c2 input gradient), "row scatter" formulation.
+//
+// An SS tcgen05.mma with N = 32 is bound by the shared-memory reads of its operands, not by the tensor
+// pipe (tools/umma_rate2.cu: 40 cycles per M128 N32 K16 against a 16-cycle tensor floor; the 4 KB A
+// tile dominates).  So instead of gathering 9 taps per OUTPUT row (18 MMAs of N = 32, every A tile read
+// three times), each INPUT row is read once per (kw, K half) and scattered to the three output rows it
+// feeds: B = [W(kh=2) | W(kh=1) | W(kh=0)] (N = 96) and D = the accumulators of output rows i-1, i, i+1,
+// which sit in CONSECUTIVE 32-column slots of a TMEM ring -- accumulators are addressed by column, so
+// the scatter costs nothing.  6 MMAs of N = 96 per input row (7 where the newest row needs its
+// accumulate flag cleared or the ring wraps) instead of 18 of N = 32: 2.1x fewer operand bytes.
+//
+// The tensor pipe's queue is about one MMA deep (tools/umma_rate3.cu): whatever the issuing thread does
+// between two tcgen05.mma -- an mbarrier wait costs ~100 cycles even when the phase is complete, a
+// tcgen05.commit ~50 -- is time the pipe idles.  Hence all hand-shakes are per QUAD of rows: slabs are
+// published and released four at a time (one per producer warp), accumulators are committed to / freed
+// by the epilogue four at a time (16-slot ring = all 512 TMEM columns), and the D / B / instruction
+// descriptor words of a batch are computed once per row.
+// Warp roles (416 threads): 0..3 producers (cp.async, zero fill = padding), 4 MMA issuer,
+// 5..12 epilogue (two warps per TMEM lane quarter, alternating output rows).
+// ================================================================================================
+constexpr int S1_ROWS = 64;         // output rows per work item (66 input rows)
+#ifndef S1_NQUAD_V
+#define S1_NQUAD_V 5
+#endif
+constexpr int S1_NQUAD = S1_NQUAD_V;   // slab ring: 5 quads = 20 input rows
+constexpr int S1_RING = 4 * S1_NQUAD;
+constexpr int S1_NACC = 16;         // accumulator ring: 16 x 32 TMEM columns, in 4 groups of 4 rows
+constexpr int S1_NGRP = S1_NACC / 4;
+constexpr int S1_EPI = 8;           // epilogue warps
+constexpr int S1_SLAB = 4 * PS;
+constexpr int S1_WN = 96 * 16;      // bytes per (kw, channel group) weight block: [3 kh slots x 32 co][8 ci]
+constexpr int S1_SMEM = W_BYTES + S1_RING * S1_SLAB + 1024;
+constexpr int S1_THREADS = 32 * (NPROD + 1 + S1_EPI);
+static_assert(NPROD == 4, "one slab of every quad per producer warp");
+
+#ifdef DD_S1_PROF
+__device__ long long g_s1_prof[148 * 16];
+#define S1_T(var) const long long var = clock64()
+#define S1_ACC(i, d) prof[i] += (d)
+#else
+#define S1_T(var)
+#define S1_ACC(i, d)
+#endif
+
+struct S1Bars {
+  uint64_t full[S1_NQUAD], empty[S1_NQUAD], acc_full[S1_NGRP], acc_empty[S1_NGRP];
+  uint32_t tmem_base;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                           const float* __restrict__ w_oihw,
+                                                                           const float* __restrict__ bias,
+                                                                           const __nv_bfloat16* __restrict__ mask,
+                                                                           __nv_bfloat16* __restrict__ out, int B, int H,
+                                                                           int W, int dbg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w = smem;
+  uint8_t* s_slab = smem + W_BYTES;
+  S1Bars* bars = reinterpret_cast<S1Bars*>(smem + W_BYTES + S1_RING * S1_SLAB);
+  __shared__ float s_bias[C];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wtiles = (W + TILE_M - 1) / TILE_M;
+  const int hsegs = (H + S1_ROWS - 1) / S1_ROWS;
+  const int items = B * wtiles * hsegs;
+
+  // weights -> bf16 B operands [kw][cg][slot = 2 - kh][co][8 ci]: slot order = ascending output row
+  for (int i = tid; i < 9 * C * C; i += S1_THREADS) {
+    const int ci = i & 31, co = (i >> 5) & 31, tap = i >> 10;
+    const int kh = tap / 3, kw = tap - 3 * kh;
+    float v;
+    if (MODE == 0) v = w_oihw[(co * C + ci) * 9 + tap];
+    else v = w_oihw[(ci * C + co) * 9 + (8 - tap)];               // dgrad: W[co=in][ci=out][flipped tap]
+    *reinterpret_cast<__nv_bfloat16*>(s_w + (kw * 4 + (ci >> 3)) * S1_WN + ((2 - kh) * 32 + co) * 16 + (ci & 7) * 2) =
+        __float2bfloat16_rn(v);
+  }
+  if (tid < C) s_bias[tid] = (MODE == 0) ? bias[tid] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < S1_NQUAD; ++i) { umma::mbar_init(&bars->full[i], 128); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < S1_NGRP; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], S1_EPI); }
+    umma::fence_mbar_init();
+  }
+  if (warp == MMA_WARP) umma::tmem_alloc(&bars->tmem_base, S1_NACC * 32);
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
+
+  if (warp < NPROD) {
+    // =========================== producers: slab g -> warp g % 4, quad g / 4 ======================
+    // Each lane's cp.async.mbarrier.arrive.noinc publishes its copies when they land (4 warps x 32
+    // lanes = the 128 arrivals of a quad), so a warp never blocks on its own loads.
+    uint32_t g = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int h0 = hs * S1_ROWS;
+      const int rows = min(S1_ROWS, H - h0);
+      const int c0 = wt * TILE_M - 1;
+      const __nv_bfloat16* img = in + (size_t)b * H * W * C;
+      for (int s = 0; s < rows + 2; ++s, ++g) {
+        if ((g & 3) != (uint32_t)warp) continue;
+        const uint32_t quad = g >> 2;
+        umma::mbar_wait(&bars->empty[quad % S1_NQUAD], ((quad / S1_NQUAD) & 1) ^ 1);
+        const int r = h0 - 1 + s;
+        const bool row_ok = (r >= 0) && (r < H);
+        if (!(dbg & 4))
+          load_slab<130, 0, PS, 32>(umma::smem_u32(s_slab + (g % S1_RING) * S1_SLAB), img + (size_t)(row_ok ? r : 0) * W * C,
+                                    row_ok, c0, W, lane);
+        umma::cp_async_mbar_arrive_noinc(&bars->full[quad % S1_NQUAD]);
+      }
+    }
+    // the last quad may be partial: its missing slabs still owe their arrivals
+    for (; (g & 3) != 0; ++g) {
+      if ((g & 3) != (uint32_t)warp) continue;
+      const uint32_t quad = g >> 2;
+      umma::mbar_wait(&bars->empty[quad % S1_NQUAD], ((quad / S1_NQUAD) & 1) ^ 1);
+      umma::cp_async_mbar_arrive_noinc(&bars->full[quad % S1_NQUAD]);
+    }
+  } else if (warp == MMA_WARP) {
+    // =========================== MMA issuer (whole warp loops, elected lane issues) ===============
+    constexpr uint32_t idesc32 = umma::make_idesc_bf16(TILE_M, 32, false, false);
+    constexpr uint32_t IDESC_NSTEP = (32u >> 3) << 17;                        // +32 columns of N
+    constexpr uint32_t ab_hi = umma::desc_hi(128);
+    const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), PS);         // A: LBO = plane stride, SBO = 128
+    const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), S1_WN);         // B: LBO = channel-group block, SBO = 128
+    uint32_t g = 0;             // slab counter
+    uint32_t rc0 = 0;           // output-row counter at the start of the item (accumulator ring position)
+#ifdef DD_S1_PROF
+    long long prof[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+#endif
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int hs = (it / wtiles) % hsegs;
+      const int rows = min(S1_ROWS, H - hs * S1_ROWS);
+      const bool last_item = it + (int)gridDim.x >= items;
+      for (int s = 0; s < rows + 2; ++s, ++g) {
+        // input row s of the item feeds output rows s-2 (kh = 2), s-1 (kh = 1), s (kh = 0)
+        S1_T(t0);
+        const bool is_new = s < rows;                     // output row s receives its first contribution
+        if ((g & 3) == 0) {                               // first slab of a quad
+          const uint32_t quad = g >> 2;
+          umma::mbar_wait(&bars->full[quad % S1_NQUAD], (quad / S1_NQUAD) & 1);
+          umma::fence_proxy_async_smem();                 // cp.async (generic proxy) writes -> UMMA (async proxy) reads
+#ifdef DD_S1_PROF
+          { const long long d = clock64() - t0; prof[2] += d; if (d > 400) prof[3] += 1; }
+#endif
+        }
+        S1_T(t0b);
+        if (is_new && ((rc0 + s) & 3) == 0) {             // first row of an accumulator group
+          const uint32_t grp = (rc0 + s) >> 2;
+          umma::mbar_wait(&bars->acc_empty[grp % S1_NGRP], ((grp / S1_NGRP) & 1) ^ 1);
+          umma::tc_fence_after_sync();
+#ifdef DD_S1_PROF
+          { const long long d = clock64() - t0b; prof[5] += d; if (d > 400) prof[3] += 1000000; }
+#endif
+        }
+        S1_T(t1);
+        const uint32_t slab_lo = a_lo0 + (g % S1_RING) * (S1_SLAB >> 4);
+        const uint32_t rc_done = rc0 + s - 2;             // output row completed by this batch (s >= 2)
+        if (umma::elect_one()) {
+          if (dbg & 1) {
+          } else if (s >= 2 && is_new) {
+            // ---- interior row (62 of 66): three output rows in ring slots sl, sl+1, sl+2; straight-line issue ----
+            const uint32_t sl = rc_done % S1_NACC;
+            const uint32_t d0 = tmem + sl * 32;
+            constexpr uint32_t i32 = idesc32, i64 = idesc32 + IDESC_NSTEP, i96 = idesc32 + 2 * IDESC_NSTEP;
+#define S1_AT(t) (slab_lo + (((((t) >> 1) * 16) + (2 * ((t) & 1)) * PS) >> 4))
+#define S1_BT(t) (b_lo0 + ((((((t) >> 1) * 4) + 2 * ((t) & 1)) * S1_WN) >> 4))
+            if (sl <= S1_NACC - 3) {
+              umma::mma_bf16_lohi(d0, S1_AT(0), ab_hi, S1_BT(0), ab_hi, i64, 1u);
+              umma::mma_bf16_lohi(d0 + 64, S1_AT(0), ab_hi, S1_BT(0) + 64, ab_hi, i32, 0u);
+#pragma unroll
+              for (int t = 1; t < 6; ++t) umma::mma_bf16_lohi(d0, S1_AT(t), ab_hi, S1_BT(t), ab_hi, i96, 1u);
+            } else if (sl == S1_NACC - 2) {               // newest row wraps to slot 0
+              umma::mma_bf16_lohi(d0, S1_AT(0), ab_hi, S1_BT(0), ab_hi, i64, 1u);
+              umma::mma_bf16_lohi(tmem, S1_AT(0), ab_hi, S1_BT(0) + 64, ab_hi, i32, 0u);
+#pragma unroll
+              for (int t = 1; t < 6; ++t) {
+                umma::mma_bf16_lohi(d0, S1_AT(t), ab_hi, S1_BT(t), ab_hi, i64, 1u);
+                umma::mma_bf16_lohi(tmem, S1_AT(t), ab_hi, S1_BT(t) + 64, ab_hi, i32, 1u);
+              }
+            } else {                                      // slots 15, 0, 1
+              umma::mma_bf16_lohi(d0, S1_AT(0), ab_hi, S1_BT(0), ab_hi, i32, 1u);
+              umma::mma_bf16_lohi(tmem, S1_AT(0), ab_hi, S1_BT(0) + 32, ab_hi, i32, 1u);
+              umma::mma_bf16_lohi(tmem + 32, S1_AT(0), ab_hi, S1_BT(0) + 64, ab_hi, i32, 0u);
+#pragma unroll
+              for (int t = 1; t < 6; ++t) {
+                umma::mma_bf16_lohi(d0, S1_AT(t), ab_hi, S1_BT(t), ab_hi, i32, 1u);
+                umma::mma_bf16_lohi(tmem, S1_AT(t), ab_hi, S1_BT(t) + 32, ab_hi, i64, 1u);
+              }
+            }
+          } else {
+            // ---- first / last two input rows of an item (or a very short item): general form ----
+            const int jlo = max(s - 2, 0), jhi = min(s, rows - 1);
+            const int n = jhi - jlo + 1;                      // output rows fed: 1..3
+            const int blk = jlo - (s - 2);                    // their first kh slot in B
+            const uint32_t sl = (rc0 + jlo) % S1_NACC;
+            const int n1 = min(n, (int)(S1_NACC - sl));       // rows before the accumulator ring wraps
+            const uint32_t d0 = tmem + sl * 32;
+            const uint32_t i0 = idesc32 + (n1 - 1) * IDESC_NSTEP, i1 = idesc32 + (n - n1 - 1) * IDESC_NSTEP;
+            const uint32_t bo0 = blk * 32, bo1 = (blk + n1) * 32;   // B start offsets (16-byte units): 32 co rows x 16 B per slot
+            const bool two = n > n1;
+            const int no = is_new ? n - 1 : n;                // rows that already hold partial sums
+            const int no1 = min(no, n1), no2 = no - no1;
+            // (kw 0, K half 0): accumulate into the older rows, overwrite the newest
+            if (no1 > 0) umma::mma_bf16_lohi(d0, slab_lo, ab_hi, b_lo0 + bo0, ab_hi, idesc32 + (no1 - 1) * IDESC_NSTEP, 1u);
+            if (no2 > 0) umma::mma_bf16_lohi(tmem, slab_lo, ab_hi, b_lo0 + bo1, ab_hi, idesc32 + (no2 - 1) * IDESC_NSTEP, 1u);
+            if (is_new)
+              umma::mma_bf16_lohi(tmem + ((rc0 + jhi) % S1_NACC) * 32, slab_lo, ab_hi, b_lo0 + (blk + n - 1) * 32, ab_hi, idesc32, 0u);
+#pragma unroll
+            for (int t = 1; t < 6; ++t) {
+              umma::mma_bf16_lohi(d0, S1_AT(t), ab_hi, S1_BT(t) + bo0, ab_hi, i0, 1u);
+              if (two) umma::mma_bf16_lohi(tmem, S1_AT(t), ab_hi, S1_BT(t) + bo1, ab_hi, i1, 1u);
+            }
+          }
+#undef S1_AT
+#undef S1_BT
+          if ((g & 3) == 3) umma::mma_commit(&bars->empty[(g >> 2) % S1_NQUAD]);          // quad of slabs consumed
+          if (s >= 2 && ((rc_done & 3) == 3 || (last_item && s == rows + 1)))              // group of output rows complete
+            umma::mma_commit(&bars->acc_full[(rc_done >> 2) % S1_NGRP]);
+        }
+        __syncwarp();
+        S1_T(t2);
+        S1_ACC(0, t1 - t0); S1_ACC(1, t2 - t1);
+      }
+      rc0 += rows;
+    }
+#ifdef DD_S1_PROF
+    if (lane == 0) {
+      prof[4] = clock64() - t_begin;
+      for (int i = 0; i < 5; ++i) g_s1_prof[blockIdx.x * 16 + i] = prof[i];
+      g_s1_prof[blockIdx.x * 16 + 5] = g;
+      g_s1_prof[blockIdx.x * 16 + 6] = prof[5];
+    }
+#endif
+  } else {
+    // =========================== epilogue (warps 5..12) ===========================================
+    // TMEM -> registers (thread = pixel) -> bias/ReLU (or ReLU mask) -> bf16 -> two 32-byte stores per thread.
+    // Shared memory is the scarce resource of this kernel (the MMA operand reads use its full bandwidth), so the
+    // epilogue stays out of it: bias lives in registers and there is no staging tile; 32-byte accesses keep
+    // every global sector whole.
+    const int quarter = warp & 3;                          // TMEM lanes [32*quarter, +32) belong to this warp
+    const int ew = warp - (NPROD + 1);
+    const uint32_t half = (uint32_t)ew >> 2;               // this warp takes output rows with (counter & 1) == half
+    float bs[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) bs[k] = s_bias[k];
+    uint32_t rc0 = 0;
+    uint32_t cur_grp = 0xffffffffu;                        // accumulator group this warp is reading
+#ifdef DD_S1_PROF
+    long long eprof[3] = {0, 0, 0};
+    const long long te_begin = clock64();
+#endif
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int h0 = hs * S1_ROWS;
+      const int rows = min(S1_ROWS, H - h0);
+      const int wo = wt * TILE_M + quarter * 32 + lane;
+      const bool ok = wo < W;
+      for (int j = (int)((rc0 ^ half) & 1); j < rows; j += 2) {
+        const uint32_t rc = rc0 + j;
+        const uint32_t buf = rc % S1_NACC;
+        const uint32_t grp = rc >> 2;
+        const size_t off = (((size_t)b * H + h0 + j) * W + (ok ? wo : 0)) * C;
+        uint32_t mk[16];
+        if (MODE == 1 && mask != nullptr && ok) {      // in flight while this warp waits for the MMAs
+          umma::ldg256(mask + off, mk);
+          umma::ldg256(mask + off + 16, mk + 8);
+        }
+        S1_T(e0);
+        if (grp != cur_grp) {
+          if (cur_grp != 0xffffffffu) {          // both rows of the previous group are in registers
+            umma::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive_relaxed(&bars->acc_empty[cur_grp % S1_NGRP]);
+          }
+          umma::mbar_wait(&bars->acc_full[grp % S1_NGRP], (grp / S1_NGRP) & 1);
+          umma::tc_fence_after_sync();
+          cur_grp = grp;
+        }
+        S1_T(e1);
+        uint32_t r[32];
+        umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * 32, r);
+        umma::tmem_ld_wait();
+        S1_T(e2);
+        if (ok && !(dbg & 2)) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float x0 = __uint_as_float(r[2 * k]), x1 = __uint_as_float(r[2 * k + 1]);
+            if (MODE == 0) { x0 = fmaxf(x0 + bs[2 * k], 0.f); x1 = fmaxf(x1 + bs[2 * k + 1], 0.f); }
+            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            pk[k] = *reinterpret_cast<uint32_t*>(&h);
+            if (MODE == 1 && mask != nullptr) {
+              const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+              pk[k] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mk[k]), zero);
+            }
+          }
+          umma::stg256(out + off, pk);
+          umma::stg256(out + off + 16, pk + 8);
+        }
+#ifdef DD_S1_PROF
+        { S1_T(e3); eprof[0] += e1 - e0; eprof[1] += e2 - e1; eprof[2] += e3 - e2; }
+#endif
+      }
+      rc0 += rows;
+    }
+    // (the last group is never waited for by the MMA warp: no arrival owed)
+#ifdef DD_S1_PROF
+    if (lane == 0 && ew == 0) {
+      g_s1_prof[blockIdx.x * 16 + 8] = eprof[0];
+      g_s1_prof[blockIdx.x * 16 + 9] = eprof[1];
+      g_s1_prof[blockIdx.x * 16 + 10] = eprof[2];
+      g_s1_prof[blockIdx.x * 16 + 11] = clock64() - te_begin;
+    }
+#endif
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) umma::tmem_dealloc(tmem, S1_NACC * 32);
+}
+
+template <int MODE>
+int launch_s1(const void* in, const float* w, const float* bias, const void* mask, void* out, int B, int H, int W,
+              cudaStream_t st) {
+  const int items = B * ((W + TILE_M - 1) / TILE_M) * ((H + S1_ROWS - 1) / S1_ROWS);
+  auto k = conv3x3_c32_s1_tc_kernel<MODE>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_SMEM);
+  if (e != cudaSuccess) return dd::fail((int)e, "conv_tc s1: cudaFuncSetAttribute(%d): %s", S1_SMEM, cudaGetErrorString(e));
+  const int grid = items < dd::kSMs ? items : dd::kSMs;
+  static const int dbg = getenv("DD_CONV_DBG") ? atoi(getenv("DD_CONV_DBG")) : 0;   // profiling aid: 1 no MMA, 2 no stores, 4 no loads
+  k<<<grid, S1_THREADS, S1_SMEM, st>>>((const __nv_bfloat16*)in, w, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H,
+                                       W, dbg);
+  return dd::check_launch("conv3x3_c32_s1_tc");
+}
+
+// ================================================================================================
 // Input gradient of the stride-2 conv (c3) = stride-2 transposed conv, on the tensor cores.
 //   dx[h,w,ci] = sum over taps with (h+1-kh), (w+1-kw) even of dy[(h+1-kh)/2,(w+1-kw)/2,:] . W[:,ci,kh,kw]
 // A CTA marches down dy rows m for a strip of 128 column PAIRS i (dx columns 2i, 2i+1).  Each m
@@ -1029,6 +1369,12 @@ __global__ void __launch_bounds__(256) c1_wgrad_tc_reduce_kernel(const float* __
 
 }  // namespace
 
+#ifdef DD_S1_PROF
+extern "C" int dd_debug_s1_prof(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, g_s1_prof, sizeof(long long) * 148 * 16);
+}
+#endif
+
 namespace dd {
 
 // mode: 0 forward, 1 input gradient, 2 weight gradient
@@ -1040,9 +1386,10 @@ bool conv_tc_supported(int H, int W, int stride, int mode) {
 
 int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int stride,
                        int mode, const void* mask, cudaStream_t st) {
-  if (mode == 0 && stride == 1) return launch<1, 0>(in, w, bias, nullptr, out, B, H, W, st);
+  static const bool old_s1 = getenv("DD_CONV_OLD_S1") != nullptr;   // A/B timing aid: the 18 x N=32 gather kernel
+  if (mode == 0 && stride == 1) return old_s1 ? launch<1, 0>(in, w, bias, nullptr, out, B, H, W, st) : launch_s1<0>(in, w, bias, nullptr, out, B, H, W, st);
   if (mode == 0 && stride == 2) return launch<2, 0>(in, w, bias, nullptr, out, B, H, W, st);
-  if (mode == 1 && stride == 1) return launch<1, 1>(in, w, nullptr, mask, out, B, H, W, st);
+  if (mode == 1 && stride == 1) return old_s1 ? launch<1, 1>(in, w, nullptr, mask, out, B, H, W, st) : launch_s1<1>(in, w, nullptr, mask, out, B, H, W, st);
   if (mode == 1 && stride == 2) {
     // here `in` = dy [B,Ho,Wo,32], `out` = dx [B,H,W,32]
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;

@@ -3,8 +3,7 @@
 mkdir -p gpurun_out
 CMD="python scripts/run_conv_kernels.py"
 REPS=2 $CMD > gpurun_out/plain_conv.log 2>&1 && \
-REPS=2 ncu --set full --clock-control none --import-source on -k regex:'conv3x3_c32_(tc|wgrad_tc|dgrad)' -s 3 -c 3 \
+REPS=2 ncu --set full --clock-control none --import-source on -k regex:'conv3x3_c32_(s1_tc|tc|wgrad_tc|dgrad)' -s 3 -c ${NCU_COUNT:-3} \
     -f -o gpurun_out/prof_conv $CMD > gpurun_out/ncu_conv.log 2>&1
 echo "ncu rc=$?"
 tail -3 gpurun_out/ncu_conv.log
-ncu -i gpurun_out/prof_conv.ncu-rep --page raw --csv > gpurun_out/prof_conv_raw.csv 2>/dev/null

@@ -1,9 +1,9 @@
 import os, sys, subprocess
 if len(sys.argv) == 1:
-    for dbg in (0, 1, 2, 3, 4, 5, 6, 7):
+    for dbg in [int(a) for a in os.environ.get('DBGS', '0 1 2 3 4 5 6 7').split()]:
         env = dict(os.environ, DD_CONV_DBG=str(dbg))
         out = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print("dbg", dbg, "(1 no MMA | 2 no stores | 4 no loads):", out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
+        print("dbg", dbg, "(1 no MMA | 2 no stores | 4 no loads):", " || ".join(out.stdout.strip().splitlines()[-2:]) if out.stdout.strip() else out.stderr[-300:])
     sys.exit(0)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -25,3 +25,15 @@ e0.record()
 for _ in range(10): run()
 e1.record(); torch.cuda.synchronize()
 print(f"{e0.elapsed_time(e1)/10:.4f} ms")
+
+import ctypes
+lib = _lib.load()
+if hasattr(lib, "dd_debug_s1_prof"):
+    buf = (ctypes.c_longlong * (148 * 16))()
+    lib.dd_debug_s1_prof(buf)
+    import statistics
+    cols = list(zip(*[buf[i * 16:(i + 1) * 16] for i in range(148)]))
+    med = [statistics.median(c) for c in cols]
+    n = med[5] or 1
+    print("PROF per input row (cycles, median CTA): waits %.0f (full %.0f, acc %.0f; blocking full %d acc %d of %d each) issue+commit %.0f | total %.0f | rows %d || epi(one warp, per its row): wait %.0f ld %.0f store %.0f total %.0f" % (
+        med[0] / n, med[2] / n, med[6] / n, med[3] % 1000000, med[3] // 1000000, n // 4, med[1] / n, med[4] / n, n, med[8] / (n / 2), med[9] / (n / 2), med[10] / (n / 2), med[11] / (n / 2)))
