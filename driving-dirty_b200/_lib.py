@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 import torch  # noqa: F401  (loads libcudart.so.12 into the process before our library)
 
@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
 DD_F32, DD_BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
-_P, _I, _L, _Z = c_void_p, c_int, c_longlong, c_size_t
+_P, _I, _L, _Z, _F = c_void_p, c_int, c_longlong, c_size_t, c_float
 
 # name -> (restype, argtypes); mirrors include/dd_b200.h declaration by declaration
 SIGNATURES = {
@@ -59,6 +59,8 @@ SIGNATURES = {
     "dd_bce_prob_workspace_bytes": (_Z, []),
     "dd_mse_fwd": (_I, [_P, _P, _P, _P, _Z, _L, _P]),
     "dd_mse_bwd": (_I, [_P, _P, _P, _P, _L, _P]),
+    "dd_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _F, _P]),
+    "dd_adam_step_sharded": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _L, _L, _F, _F, _F, _F, _F, _L, _F, _I, _P]),
 }
 
 

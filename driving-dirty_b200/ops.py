@@ -206,8 +206,9 @@ class SkinnyLinear(torch.autograd.Function):
     weight-streaming kernels (x is read as fp32)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, impl):
+    def forward(ctx, x, w, b, impl, grad_buffer=None, grad_ready=None):
         _require_cuda(x, w)
+        ctx.grad_buffer, ctx.grad_ready = grad_buffer, grad_ready
         x, wd = _c(x), _c(w.detach())
         if wd.dtype != torch.float32:
             wd = wd.float()
@@ -240,13 +241,20 @@ class SkinnyLinear(torch.autograd.Function):
             call("dd_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), dtype_code(ctx.x_dtype), ws.data_ptr(), n,
                  B, N, K, ctx.impl, st)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
+            # a parameter claimed by optim.FusedAdam's sharded update owns a persistent (peer-mapped) gradient
+            # buffer: the kernel writes there and autograd gets no tensor to clone or accumulate
+            direct = ctx.grad_buffer is not None
+            dw = ctx.grad_buffer if direct else torch.empty_like(w)
             db = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_bias else None
             call("dd_linear_wgrad", dy.data_ptr(), x.data_ptr(), dtype_code(x.dtype), dw.data_ptr(),
                  db.data_ptr() if db is not None else None, B, N, K, ctx.impl, st)
+            if direct:
+                dw = None
+                if ctx.grad_ready is not None:
+                    ctx.grad_ready()
         elif ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0)
-        return dx, dw, db, None
+        return dx, dw, db, None, None, None
 
 
 def linear(x, weight, bias=None, impl=IMPL_AUTO, allow_tf32=False):
@@ -258,7 +266,10 @@ def linear(x, weight, bias=None, impl=IMPL_AUTO, allow_tf32=False):
         fast = (x.dtype == torch.bfloat16 or allow_tf32) and x.is_cuda and \
             bool(_lib.load().dd_linear_tc_supported(B, weight.shape[0], K))
         impl = _lib.IMPL_TCGEN05 if fast else _lib.IMPL_SIMT
-    return SkinnyLinear.apply(x, weight, bias, impl)
+    buf = getattr(weight, "_dd_grad_buffer", None)
+    if buf is not None and not (buf.shape == weight.shape and buf.dtype == torch.float32 and buf.is_contiguous()):
+        raise RuntimeError("linear: weight._dd_grad_buffer does not match the weight")
+    return SkinnyLinear.apply(x, weight, bias, impl, buf, getattr(weight, "_dd_grad_ready", None) if buf is not None else None)
 
 
 # --------------------------------------------------------------------------------------------
@@ -510,7 +521,7 @@ class Conv2dNHWC(torch.autograd.Function):
             db = torch.empty(desc.Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
             call("dd_conv2d_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr() if db is not None else None,
                  ctypes.byref(desc), code, ws.data_ptr(), n, st)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2

@@ -182,6 +182,30 @@ int dd_mse_fwd(const float* y, const float* y_hat, float* loss, void* workspace,
 int dd_mse_bwd(const float* y, const float* y_hat, const float* grad_out, float* dy_hat,
                long long n, void* stream);
 
+/* ---- A12 / 8(f): optimizer step ---------------------------------------------------------------
+ * torch.optim.Adam(params, lr) at roadmap_bce_v2.py:155, autoencoder.py:120 (amsgrad off; weight_decay
+ * is the L2 form added to the gradient).  One launch per tensor: param -= lr/(1-b1^t) * m / (sqrt(v)/
+ * sqrt(1-b2^t) + eps) with m, v updated in place; `step` = t >= 1; the gradient is read as
+ * grad * grad_scale.  All pointers fp32. */
+int dd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
+                 float grad_scale, void* stream);
+/* Data-parallel form (replaces Lightning ddp's gradient all-reduce + the N identical Adam updates):
+ * this rank updates elements [shard_offset, shard_offset + shard_numel) of a parameter whose `world`
+ * gradient / weight replicas are peer-mapped at grad_replicas[k] / param_replicas[k] (HOST arrays of
+ * device pointers, index = rank).  The gradient is the SUM of the replicas times grad_scale (pass
+ * 1/world for the mean); the new weights are written to every replica.  mc_grad / mc_param: NVLink
+ * multicast addresses of the same buffers (both or neither; NULL = peer loads / stores).  exp_avg /
+ * exp_avg_sq hold the shard only.  The caller puts a cross-rank barrier before (gradients complete)
+ * and after (weights landed) on the same stream.  ctas_per_sm: 1..8 update CTAs (256 threads) per SM;
+ * 1 leaves room for a persistent conv CTA beside each when the update overlaps the backward pass. */
+int dd_adam_step_sharded(const void* const* grad_replicas, void* const* param_replicas,
+                         const void* mc_grad, void* mc_param, int world, int rank,
+                         float* exp_avg_shard, float* exp_avg_sq_shard, long long shard_offset,
+                         long long shard_numel, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, long long step, float grad_scale, int ctas_per_sm,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif
