@@ -194,6 +194,15 @@ extern "C" int dd_adam_step_sharded(const void* const* grad_replicas, void* cons
   const long long want = ((shard_numel >> 2) + kThreads - 1) / kThreads;
   const long long cap = (long long)dd::kSMs * (ctas_per_sm >= 1 && ctas_per_sm <= 8 ? ctas_per_sm : 8);
   const int grid = (int)(want < cap ? want : cap);
+  // An SM's L1 / shared-memory split only changes when the SM is idle: with the default carveout (all L1 for a kernel that
+  // uses no shared memory) the persistent conv kernels of the backward pass (90-210 KB of shared memory per CTA) could not
+  // join an SM that runs an update CTA and queued behind the whole update (1.2 ms gap seen in the step timeline).
+  static const bool carveout_set = [] {
+    cudaFuncSetAttribute(adam_kernel<1, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(adam_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)carveout_set;
   if (mc_grad && mc_param)
     adam_kernel<2, 4><<<grid, kThreads, 0, st>>>(pp, (const float*)mc_grad, (float*)mc_param, exp_avg_shard, exp_avg_sq_shard,
                                               shard_offset, shard_numel, world, rank, h);

@@ -642,7 +642,7 @@ struct DgBars {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_dgrad_s2_tc_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                                const float* __restrict__ w_oihw,
                                                                                const __nv_bfloat16* __restrict__ mask,
                                                                                __nv_bfloat16* __restrict__ dx, int B,

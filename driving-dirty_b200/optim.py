@@ -2,19 +2,25 @@
 roadmap_bce_v2.py:155 / autoencoder.py:120, stepped by Lightning after ddp's gradient all-reduce).
 
 One process per GPU.  With world size 1 every tensor is updated by one ``dd_adam_step`` launch.
-With world size N the two wide FC weights (> 99.9 % of the parameters) are *sharded across ranks
-for the update only*: their gradient and weight replicas live in one symmetric-memory buffer per
-rank (``torch.distributed._symmetric_memory``: every replica is peer-mapped into every process,
-plus an NVLink multicast mapping where the fabric has one), the weight-gradient kernels write
-straight into that buffer, and ``dd_adam_step_sharded`` does reduce + Adam + all-gather in ONE kernel
-(csrc/adam.cu): 1/N of the optimizer state, 1/N of the optimizer's HBM traffic, and no NCCL kernel
-competing with the persistent conv kernels for SMs during the backward pass.  The remaining small
-tensors are averaged with one flat NCCL all-reduce and updated locally.
+With world size N the parameters are *sharded across ranks for the update only*: gradient and
+weight replicas live in one symmetric-memory buffer per rank
+(``torch.distributed._symmetric_memory``: every replica is peer-mapped into every process, plus an
+NVLink multicast mapping where the fabric has one), and ``dd_adam_step_sharded`` does reduce + Adam
++ all-gather in ONE kernel (csrc/adam.cu): 1/N of the optimizer state and of the optimizer's HBM
+traffic per GPU, and no NCCL kernel in the step.
+
+* The wide FC weights (>= ``shard_min_numel`` elements; > 99.9 % of the bytes) each own a region;
+  ``ops.linear``'s weight-gradient kernel writes straight into the gradient replica (``p.grad`` is a
+  persistent view that every backward pass OVERWRITES; ``zero_grad`` leaves it in place).  With
+  ``overlap_backward=True`` their update is launched from the backward pass itself, as soon as the
+  gradient is written, on a side stream with one small CTA per SM that co-resides with the
+  persistent conv kernels of the remaining backward pass; ``step()`` joins it.
+* All other tensors share one flat region: their gradients are gathered into it by one multi-tensor
+  copy and updated by one sharded launch in ``step()``.
 
 Semantics are torch.optim.Adam's (amsgrad off, L2 weight decay); ``param_groups[i]['lr']`` is read
-every step, so ``ReduceLROnPlateau`` (roadmap_bce_v2.py:156) works unchanged.  For a sharded
-parameter ``p.grad`` is a persistent view of the symmetric buffer that each backward pass
-OVERWRITES (no accumulation across backward calls); ``zero_grad`` leaves it in place.
+every step, so ``ReduceLROnPlateau`` (roadmap_bce_v2.py:156) works unchanged; tensors whose
+gradient is ``None`` are skipped.
 """
 from __future__ import annotations
 
@@ -25,6 +31,8 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import call, stream_ptr
+
+_ALIGN = 64          # elements: every tensor of the flat region starts on a 256-byte boundary
 
 
 def shard_bounds(numel: int, world: int, rank: int):
@@ -37,6 +45,15 @@ def shard_bounds(numel: int, world: int, rank: int):
     return 4 * lo, 4 * hi
 
 
+def flat_layout(numels, align: int = _ALIGN):
+    """Offsets of tensors packed into one flat region (each start aligned) and the region's length."""
+    offs, off = [], 0
+    for n in numels:
+        offs.append(off)
+        off += -(-n // align) * align
+    return offs, off
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
                  shard_min_numel: int = 1 << 20, multicast: bool | None = None, broadcast_init: bool = True,
@@ -44,14 +61,18 @@ class FusedAdam(torch.optim.Optimizer):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) > 1 and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            raise NotImplementedError("FusedAdam: the sharded form supports one parameter group")
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
-        self._sharded = {}          # id(param) -> dict(off, n, lo, hi)
+        self._regions = {}          # id(param) -> region dict of a wide tensor
+        self._flat = None           # region dict of the flat bucket
         self._symm = None
         self._overlap = bool(overlap_backward)
         self._side = None           # stream of the updates launched from the backward pass
-        self._launched = set()      # ids of sharded params already updated for the coming step()
+        self._written = set()       # ids of wide params whose gradient replica was written since the last step()
+        self._launched = set()      # ... and whose update is already running on the side stream
         self._lib = _lib.load()     # raises when the CUDA library is missing: no fallback
         for g in self.param_groups:
             for p in g["params"]:
@@ -63,42 +84,49 @@ class FusedAdam(torch.optim.Optimizer):
     # ------------------------------------------------------------------------------------------
     def _setup_sharding(self, shard_min_numel, multicast, broadcast_init):
         import torch.distributed._symmetric_memory as symm_mem
-        big = [p for g in self.param_groups for p in g["params"]
-               if p.requires_grad and p.numel() >= shard_min_numel and p.numel() % 4 == 0]
+        params = [p for g in self.param_groups for p in g["params"]]
         if broadcast_init:          # replicas must start identical (Lightning ddp broadcasts rank 0's weights)
-            for g in self.param_groups:
-                for p in g["params"]:
-                    dist.broadcast(p.data, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
-        if not big:
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            for p in params:
+                dist.broadcast(p.data, src=src, group=self.group)
+        wide = [p for p in params if p.numel() >= shard_min_numel and p.numel() % 4 == 0]
+        small = [p for p in params if not any(p is q for q in wide)]
+        offs, flat_off = flat_layout([p.numel() for p in wide])
+        small_offs, small_total = flat_layout([p.numel() for p in small])
+        total = flat_off + small_total
+        if total == 0:
             return
-        total = sum(p.numel() for p in big)
-        dev = big[0].device
+        dev = params[0].device
         buf = symm_mem.empty(2 * total, dtype=torch.float32, device=dev)      # [gradients | weights]
         grp = self.group if self.group is not None else dist.group.WORLD
         hdl = symm_mem.rendezvous(buf, grp)
         buf.zero_()
-        off = 0
-        for p in big:
+
+        def adopt(p, off):
             n = p.numel()
             w = buf[total + off: total + off + n].view_as(p)
             w.copy_(p.data)
             p.data = w                                   # the module now computes from the symmetric replica
-            gview = buf[off: off + n].view_as(p)
+            return buf[off: off + n].view_as(p)
+
+        for p, off in zip(wide, offs):
+            gview = adopt(p, off)
             p.grad = gview
-            p._dd_grad_buffer = gview                    # ops.linear's weight-gradient kernel writes here
-            lo, hi = shard_bounds(n, self.world, self.rank)
-            self._sharded[id(p)] = dict(off=off, n=n, lo=lo, hi=hi, channel=len(self._sharded), param=p)
-            if self._overlap:                            # ops.linear calls this right after the gradient is written
-                p._dd_grad_ready = (lambda q: (lambda: self._update_in_backward(q)))(p)
-            off += n
-        ptrs = [int(x) for x in hdl.buffer_ptrs]
+            p._dd_grad_buffer = gview                    # ops.linear's weight-gradient kernel writes here ...
+            p._dd_grad_ready = (lambda q: (lambda: self._on_grad_written(q)))(p)     # ... and then calls this
+            lo, hi = shard_bounds(p.numel(), self.world, self.rank)
+            self._regions[id(p)] = dict(off=off, lo=lo, hi=hi, channel=1 + len(self._regions), key=p)
+        if small:
+            views = [adopt(p, flat_off + o) for p, o in zip(small, small_offs)]
+            lo, hi = shard_bounds(small_total, self.world, self.rank)
+            self._flat = dict(off=flat_off, lo=lo, hi=hi, channel=0, params=small, grad_views=views, key="flat")
         # per NVLink direction and GPU the multicast form moves n(1 + 1/N) bytes (the switch also loops the own replica
-        # back), peer loads / stores 2n(N-1)/N: multicast wins from N = 3 on (measured at N = 2: 3.5 ms vs 2.3 ms)
+        # back), peer loads / stores 2n(N-1)/N: multicast wins from N = 3 on (measured at N = 2: 3.5 ms vs 2.1 ms)
         want_mc = (self.world > 2) if multicast is None else bool(multicast)
         mc = int(hdl.multicast_ptr) if (want_mc and hdl.has_multicast_support) else 0
         if multicast is True and mc == 0:
             raise RuntimeError("FusedAdam: multicast requested but the symmetric buffer has no multicast mapping")
-        self._symm = dict(buf=buf, hdl=hdl, total=total, ptrs=ptrs, mc=mc)
+        self._symm = dict(buf=buf, hdl=hdl, total=total, ptrs=[int(x) for x in hdl.buffer_ptrs], mc=mc)
         if self._overlap:
             self._side = torch.cuda.Stream(device=dev)
         torch.cuda.synchronize()
@@ -112,7 +140,7 @@ class FusedAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True):
         for g in self.param_groups:
             for p in g["params"]:
-                if id(p) in self._sharded:       # persistent view of the symmetric buffer, overwritten by every backward
+                if id(p) in self._regions:       # persistent view of the symmetric buffer, overwritten by every backward
                     continue
                 if p.grad is None:
                     continue
@@ -122,13 +150,17 @@ class FusedAdam(torch.optim.Optimizer):
                     p.grad.detach_()
                     p.grad.zero_()
 
-    def _state(self, p, numel):
-        st = self.state[p]
+    def _state(self, key, numel, device):
+        st = self.state[key]
         if not st:
             st["step"] = 0
-            st["exp_avg"] = torch.zeros(numel, dtype=torch.float32, device=p.device)
-            st["exp_avg_sq"] = torch.zeros(numel, dtype=torch.float32, device=p.device)
+            st["exp_avg"] = torch.zeros(numel, dtype=torch.float32, device=device)
+            st["exp_avg_sq"] = torch.zeros(numel, dtype=torch.float32, device=device)
         return st
+
+    def _hyper(self):
+        g = self.param_groups[0]
+        return (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -136,76 +168,77 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        st_ptr = stream_ptr()
-        # ---- small / unsharded tensors: one flat averaged bucket, then one launch per tensor ----
-        local = [(g, p) for g in self.param_groups for p in g["params"] if id(p) not in self._sharded and p.grad is not None]
-        grads = {}
-        if self.world > 1 and local:
-            flat = torch.cat([p.grad.reshape(-1) for _, p in local])
-            nccl = dist.get_backend(self.group) == "nccl"
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, group=self.group)
-            if not nccl:
-                flat.div_(self.world)
-            off = 0
-            for _, p in local:
-                grads[id(p)] = flat[off: off + p.numel()]
-                off += p.numel()
-        for g, p in local:
-            grad = grads.get(id(p), p.grad)
-            if not (grad.is_contiguous() and grad.dtype == torch.float32):
-                grad = grad.contiguous().float()
-            st = self._state(p, p.numel())
-            st["step"] += 1
-            call("dd_adam_step", p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                 p.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                 float(g["weight_decay"]), st["step"], 1.0, st_ptr)
-        # ---- sharded tensors: barrier | reduce + Adam + all-gather in one kernel per tensor | barrier ----
-        if self._sharded:
-            todo = [info for key, info in self._sharded.items() if key not in self._launched]
-            if todo:
-                hdl = self._symm["hdl"]
-                hdl.barrier()                              # every rank's backward has written its gradient replica
-                for info in todo:
-                    self._launch_sharded(info, ctas_per_sm=8)
-                hdl.barrier()                              # every replica holds the new weights
-            if self._launched:
-                torch.cuda.current_stream().wait_stream(self._side)
-                self._launched.clear()
+        if self.world == 1:
+            st_ptr = stream_ptr()
+            for g in self.param_groups:
+                for p in g["params"]:
+                    if p.grad is None:
+                        continue
+                    grad = p.grad
+                    if not (grad.is_contiguous() and grad.dtype == torch.float32):
+                        grad = grad.contiguous().float()
+                    st = self._state(p, p.numel(), p.device)
+                    st["step"] += 1
+                    call("dd_adam_step", p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                         p.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                         float(g["weight_decay"]), st["step"], 1.0, st_ptr)
+            return loss
+        if self._symm is None:
+            return loss
+        hdl = self._symm["hdl"]
+        todo = [r for key, r in self._regions.items() if key in self._written and key not in self._launched]
+        fl = self._flat
+        if fl is not None:
+            have = [p.grad is not None for p in fl["params"]]
+            if any(have):
+                if not all(have):
+                    # torch.optim.Adam skips tensors without a gradient; one bucket = one step counter, so a partly
+                    # frozen bucket has no faithful sharded form
+                    raise NotImplementedError("FusedAdam (world > 1): every tensor of the flat bucket needs a gradient, or none")
+                torch._foreach_copy_(fl["grad_views"], [p.grad for p in fl["params"]])
+                todo.append(fl)
+        if todo:
+            hdl.barrier()                                  # every rank has written its gradient replicas
+            for r in todo:
+                self._launch_sharded(r, ctas_per_sm=8)
+            hdl.barrier()                                  # every replica holds the new weights
+        if self._launched:
+            torch.cuda.current_stream().wait_stream(self._side)
+        self._launched.clear()
+        self._written.clear()
         return loss
 
-    def _group_of(self, p):
-        for g in self.param_groups:
-            if any(q is p for q in g["params"]):
-                return g
-        raise KeyError("parameter is not in this optimizer")
-
-    def _launch_sharded(self, info, ctas_per_sm):
-        p, sy, W = info["param"], self._symm, self.world
-        g = self._group_of(p)
-        lo, hi, total = info["lo"], info["hi"], sy["total"]
-        st = self._state(p, hi - lo)
+    def _launch_sharded(self, r, ctas_per_sm):
+        sy, W = self._symm, self.world
+        lo, hi, total = r["lo"], r["hi"], sy["total"]
+        st = self._state(r["key"], hi - lo, sy["buf"].device)
         st["step"] += 1
-        gptrs = (ctypes.c_void_p * W)(*[b + 4 * info["off"] for b in sy["ptrs"]])
-        wptrs = (ctypes.c_void_p * W)(*[b + 4 * (total + info["off"]) for b in sy["ptrs"]])
-        mcg = ctypes.c_void_p(sy["mc"] + 4 * info["off"]) if sy["mc"] else None
-        mcw = ctypes.c_void_p(sy["mc"] + 4 * (total + info["off"])) if sy["mc"] else None
+        gptrs = (ctypes.c_void_p * W)(*[b + 4 * r["off"] for b in sy["ptrs"]])
+        wptrs = (ctypes.c_void_p * W)(*[b + 4 * (total + r["off"]) for b in sy["ptrs"]])
+        mcg = ctypes.c_void_p(sy["mc"] + 4 * r["off"]) if sy["mc"] else None
+        mcw = ctypes.c_void_p(sy["mc"] + 4 * (total + r["off"])) if sy["mc"] else None
+        lr, b1, b2, eps, wd = self._hyper()
         call("dd_adam_step_sharded", gptrs, wptrs, mcg, mcw, W, self.rank, st["exp_avg"].data_ptr(),
-             st["exp_avg_sq"].data_ptr(), lo, hi - lo, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
-             float(g["eps"]), float(g["weight_decay"]), st["step"], 1.0 / W, int(ctas_per_sm), stream_ptr())
+             st["exp_avg_sq"].data_ptr(), lo, hi - lo, lr, b1, b2, eps, wd, st["step"], 1.0 / W, int(ctas_per_sm), stream_ptr())
 
     @torch.no_grad()
-    def _update_in_backward(self, p):
-        """overlap_backward: called by ops.linear's backward as soon as p's gradient replica is written.  The reduce +
-        Adam + all-gather kernel runs on a side stream, one 256-thread CTA per SM beside the persistent conv kernels of
-        the rest of the backward pass; step() joins the side stream.  (The weights change before step() is called:
-        only for training loops that step after every backward, like the reference's.)"""
-        info = self._sharded[id(p)]
-        if id(p) in self._launched:
-            raise RuntimeError("FusedAdam(overlap_backward=True): two backward passes without a step()")
+    def _on_grad_written(self, p):
+        """Called by ops.linear's backward right after p's gradient replica is written.  overlap_backward: the reduce
+        + Adam + all-gather kernel is launched here, on a side stream, one 256-thread CTA per SM beside the persistent
+        conv kernels of the rest of the backward pass; step() joins the side stream.  (The weights then change before
+        step() is called: for training loops that step after every backward, like the reference's.)"""
+        key = id(p)
+        if key in self._written:
+            raise RuntimeError("FusedAdam: two backward passes wrote the gradient of a sharded parameter without a "
+                               "step() in between (its gradient buffer is overwritten, not accumulated)")
+        self._written.add(key)
+        if not self._overlap:
+            return
+        r = self._regions[key]
         hdl = self._symm["hdl"]
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
-            hdl.barrier(channel=info["channel"])
-            self._launch_sharded(info, ctas_per_sm=1)
-            hdl.barrier(channel=info["channel"])
-        self._launched.add(id(p))
+            hdl.barrier(channel=r["channel"])
+            self._launch_sharded(r, ctas_per_sm=1)
+            hdl.barrier(channel=r["channel"])
+        self._launched.add(key)

@@ -29,16 +29,20 @@ def timeit(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-t_step = timeit(opt.step)
-msg = f"rank {rank}/{world} multicast={opt.uses_multicast}: opt.step {t_step:.3f} ms"
+ctas = int(os.environ.get("CTAS", 0))
+if ctas and world > 1:
+    orig = opt._launch_sharded
+    opt._launch_sharded = lambda info, ctas_per_sm: orig(info, ctas)
+def full_step():
+    opt._written.update(opt._regions.keys())     # as if this backward pass had written every wide gradient
+    opt.step()
+t_step = timeit(full_step)
+msg = f"rank {rank}/{world} multicast={opt.uses_multicast} ctas/SM={ctas or 8}: opt.step {t_step:.3f} ms"
 if world > 1:
     sy = opt._symm
     t_bar = timeit(lambda: sy["hdl"].barrier())
     msg += f" | symm barrier {t_bar:.3f} ms"
-    def small():
-        flat = torch.cat([p.grad.reshape(-1) for p in params[2:]])
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-    msg += f" | small bucket cat+allreduce {timeit(small):.3f} ms"
+    msg += f" | flat bucket only {timeit(opt.step):.3f} ms"
 else:
     ref = [torch.nn.Parameter(p.detach().clone()) for p in params]
     for a, b in zip(ref, params): a.grad = b.grad.clone()
