@@ -23,6 +23,7 @@
 #include "dd_common.cuh"
 #include <stdlib.h>
 
+#include "tma_host.h"
 #include "umma.cuh"
 
 namespace {
@@ -315,7 +316,9 @@ constexpr int S1_RING = 4 * S1_NQUAD;
 constexpr int S1_NACC = 16;         // accumulator ring: 16 x 32 TMEM columns, in 4 groups of 4 rows
 constexpr int S1_NGRP = S1_NACC / 4;
 constexpr int S1_EPI = 8;           // epilogue warps
-constexpr int S1_SLAB = 4 * PS;
+constexpr int S1_PS = PS;            // plane stride 2176 B = 17 x 128 (TMA destinations are 128-byte aligned); a box fills 2080 B
+constexpr int S1_SLAB = 4 * S1_PS;
+constexpr int S1_SLAB_TX = 4 * 130 * 16;   // bytes one input row's four boxes deliver
 constexpr int S1_WN = 96 * 16;      // bytes per (kw, channel group) weight block: [3 kh slots x 32 co][8 ci]
 constexpr int S1_SMEM = W_BYTES + S1_RING * S1_SLAB + 1024;
 constexpr int S1_THREADS = 32 * (NPROD + 1 + S1_EPI);
@@ -336,7 +339,7 @@ struct S1Bars {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const __nv_bfloat16* __restrict__ in,
+__global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const __grid_constant__ CUtensorMap map_in,
                                                                            const float* __restrict__ w_oihw,
                                                                            const float* __restrict__ bias,
                                                                            const __nv_bfloat16* __restrict__ mask,
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
   }
   if (tid < C) s_bias[tid] = (MODE == 0) ? bias[tid] : 0.f;
   if (tid == 0) {
-    for (int i = 0; i < S1_NQUAD; ++i) { umma::mbar_init(&bars->full[i], 128); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < S1_NQUAD; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < S1_NGRP; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], S1_EPI); }
     umma::fence_mbar_init();
   }
@@ -378,41 +381,42 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
   const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
   if (warp < NPROD) {
-    // =========================== producers: slab g -> warp g % 4, quad g / 4 ======================
-    // Each lane's cp.async.mbarrier.arrive.noinc publishes its copies when they land (4 warps x 32
-    // lanes = the 128 arrivals of a quad), so a warp never blocks on its own loads.
-    uint32_t g = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
-      const int h0 = hs * S1_ROWS;
-      const int rows = min(S1_ROWS, H - h0);
-      const int c0 = wt * TILE_M - 1;
-      const __nv_bfloat16* img = in + (size_t)b * H * W * C;
-      for (int s = 0; s < rows + 2; ++s, ++g) {
-        if ((g & 3) != (uint32_t)warp) continue;
-        const uint32_t quad = g >> 2;
-        umma::mbar_wait(&bars->empty[quad % S1_NQUAD], ((quad / S1_NQUAD) & 1) ^ 1);
-        const int r = h0 - 1 + s;
-        const bool row_ok = (r >= 0) && (r < H);
-        if (!(dbg & 4))
-          load_slab<130, 0, PS, 32>(umma::smem_u32(s_slab + (g % S1_RING) * S1_SLAB), img + (size_t)(row_ok ? r : 0) * W * C,
-                                    row_ok, c0, W, lane);
-        umma::cp_async_mbar_arrive_noinc(&bars->full[quad % S1_NQUAD]);
+    // =========================== producer: one thread of warp 0, TMA (warps 1..3 idle) ============
+    // cp.async (LDGSTS) tops out near 25-30 KB in flight per SM (every conv kernel fed that way sat at 35-50 % of
+    // HBM bandwidth with its producer warps stalled issuing copies); TMA takes a whole input row per instruction
+    // group and keeps the full ring in flight.  Four boxes per row (one per channel group: [130 px][8 ch] planes);
+    // coordinates outside the image are zero-filled by the TMA unit = the conv padding.  One mbarrier per quad of
+    // rows: expect_tx for the 16 boxes, then the loads.
+    if (warp == 0 && lane == 0) {
+      umma::tma_prefetch_desc(&map_in);
+      uint32_t g = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+        const int h0 = hs * S1_ROWS;
+        const int rows = min(S1_ROWS, H - h0);
+        const int c0 = wt * TILE_M - 1;
+        const bool last_item = it + (int)gridDim.x >= items;
+        for (int s = 0; s < rows + 2; ++s, ++g) {
+          const uint32_t quad = g >> 2;
+          uint64_t* full = &bars->full[quad % S1_NQUAD];
+          if ((g & 3) == 0) {
+            umma::mbar_wait(&bars->empty[quad % S1_NQUAD], ((quad / S1_NQUAD) & 1) ^ 1);
+            // slabs of this quad that exist: all four unless the CTA's work ends inside it
+            const int left = last_item ? rows + 2 - s : 4;
+            umma::mbar_expect_tx(full, (uint32_t)(min(left, 4) * S1_SLAB_TX));
+          }
+          const uint32_t dst = umma::smem_u32(s_slab + (g % S1_RING) * S1_SLAB);
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) umma::tma_load_4d(dst + cg * S1_PS, &map_in, cg * 8, c0, h0 - 1 + s, b, full);
+        }
       }
-    }
-    // the last quad may be partial: its missing slabs still owe their arrivals
-    for (; (g & 3) != 0; ++g) {
-      if ((g & 3) != (uint32_t)warp) continue;
-      const uint32_t quad = g >> 2;
-      umma::mbar_wait(&bars->empty[quad % S1_NQUAD], ((quad / S1_NQUAD) & 1) ^ 1);
-      umma::cp_async_mbar_arrive_noinc(&bars->full[quad % S1_NQUAD]);
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer (whole warp loops, elected lane issues) ===============
     constexpr uint32_t idesc32 = umma::make_idesc_bf16(TILE_M, 32, false, false);
     constexpr uint32_t IDESC_NSTEP = (32u >> 3) << 17;                        // +32 columns of N
     constexpr uint32_t ab_hi = umma::desc_hi(128);
-    const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), PS);         // A: LBO = plane stride, SBO = 128
+    const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), S1_PS);      // A: LBO = plane stride, SBO = 128
     const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), S1_WN);         // B: LBO = channel-group block, SBO = 128
     uint32_t g = 0;             // slab counter
     uint32_t rc0 = 0;           // output-row counter at the start of the item (accumulator ring position)
@@ -430,8 +434,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
         const bool is_new = s < rows;                     // output row s receives its first contribution
         if ((g & 3) == 0) {                               // first slab of a quad
           const uint32_t quad = g >> 2;
-          umma::mbar_wait(&bars->full[quad % S1_NQUAD], (quad / S1_NQUAD) & 1);
-          umma::fence_proxy_async_smem();                 // cp.async (generic proxy) writes -> UMMA (async proxy) reads
+          umma::mbar_wait(&bars->full[quad % S1_NQUAD], (quad / S1_NQUAD) & 1);   // TMA writes: async proxy, no fence needed
 #ifdef DD_S1_PROF
           { const long long d = clock64() - t0; prof[2] += d; if (d > 400) prof[3] += 1; }
 #endif
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
             const uint32_t sl = rc_done % S1_NACC;
             const uint32_t d0 = tmem + sl * 32;
             constexpr uint32_t i32 = idesc32, i64 = idesc32 + IDESC_NSTEP, i96 = idesc32 + 2 * IDESC_NSTEP;
-#define S1_AT(t) (slab_lo + (((((t) >> 1) * 16) + (2 * ((t) & 1)) * PS) >> 4))
+#define S1_AT(t) (slab_lo + (((((t) >> 1) * 16) + (2 * ((t) & 1)) * S1_PS) >> 4))
 #define S1_BT(t) (b_lo0 + ((((((t) >> 1) * 4) + 2 * ((t) & 1)) * S1_WN) >> 4))
             if (sl <= S1_NACC - 3) {
               umma::mma_bf16_lohi(d0, S1_AT(0), ab_hi, S1_BT(0), ab_hi, i64, 1u);
@@ -619,9 +622,12 @@ int launch_s1(const void* in, const float* w, const float* bias, const void* mas
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_SMEM);
   if (e != cudaSuccess) return dd::fail((int)e, "conv_tc s1: cudaFuncSetAttribute(%d): %s", S1_SMEM, cudaGetErrorString(e));
   const int grid = items < dd::kSMs ? items : dd::kSMs;
-  static const int dbg = getenv("DD_CONV_DBG") ? atoi(getenv("DD_CONV_DBG")) : 0;   // profiling aid: 1 no MMA, 2 no stores, 4 no loads
-  k<<<grid, S1_THREADS, S1_SMEM, st>>>((const __nv_bfloat16*)in, w, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H,
-                                       W, dbg);
+  static const int dbg = getenv("DD_CONV_DBG") ? atoi(getenv("DD_CONV_DBG")) : 0;   // profiling aid: 1 no MMA, 2 no stores
+  if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return dd::fail(DD_ERR_ALIGNMENT, "conv_tc s1: input is not 16-byte aligned");
+  CUtensorMap map;
+  if (int r = dd::tma_map_nhwc_c8(&map, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, 130))
+    return dd::fail(DD_ERR_UNSUPPORTED, "conv_tc s1: cuTensorMapEncodeTiled -> %d (B %d H %d W %d)", r, B, H, W);
+  k<<<grid, S1_THREADS, S1_SMEM, st>>>(map, w, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H, W, dbg);
   return dd::check_launch("conv3x3_c32_s1_tc");
 }
 
@@ -829,19 +835,24 @@ template <int STRIDE>
 struct WgGeo {
   static constexpr int ROWS = STRIDE == 1 ? 4 : 1;            // dy rows per stage
   static constexpr int XROWS = STRIDE == 1 ? 6 : 3;           // x rows loaded per stage
-  static constexpr int XROWS_ALLOC = STRIDE == 1 ? 6 : 4;
+  // stride 2: the A operand spans 4 rows but only 3 are stored; the 4th (junk, feeds only the unused D block) reads
+  // whatever follows in the stage -- the next parity's rows or the dy planes
+  static constexpr int XROWS_ALLOC = STRIDE == 1 ? 6 : 3;
+  // Stages in flight (stride 1: 2 x 85 KB; stride 2: 3 x 59 KB).  Smaller stride-1 stages (2 dy + 4 x rows, 4 deep) were
+  // measured slower (0.87 vs 0.77 ms): the cp.async producers, not the stage count, bound this kernel.
+  static constexpr int NST = STRIDE == 1 ? 2 : 3;
   static constexpr int XPIX = STRIDE == 1 ? 130 : 257;        // x pixels per row
   static constexpr int X_BYTES = STRIDE * XROWS_ALLOC * 4 * PS;
   static constexpr int DY_BYTES = ROWS * 4 * PSD;
   static constexpr int STAGE_BYTES = X_BYTES + DY_BYTES;
-  static constexpr int SMEM = 2 * STAGE_BYTES + 1024;
+  static constexpr int SMEM = NST * STAGE_BYTES + 1024;
   static constexpr int NQ = STRIDE == 1 ? 2 : 1;              // q slots in the per-CTA partials
   static constexpr int PARTIAL = NQ * 9 * C * C;              // floats per CTA
   static constexpr int N = 32 * NQ;
 };
 
 struct WgBars {
-  uint64_t full[2], empty[2], done;
+  uint64_t full[4], empty[4], done;
   uint32_t tmem_base;
 };
 
@@ -855,7 +866,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
   constexpr int WG_ROWS = G::ROWS, WG_XROWS = G::XROWS, WG_X_BYTES = G::X_BYTES, WG_STAGE_BYTES = G::STAGE_BYTES;
   constexpr int WG_PARTIAL = G::PARTIAL;
   extern __shared__ __align__(1024) uint8_t smem[];
-  WgBars* bars = reinterpret_cast<WgBars*>(smem + 2 * WG_STAGE_BYTES);
+  WgBars* bars = reinterpret_cast<WgBars*>(smem + G::NST * WG_STAGE_BYTES);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role code stays on the uniform datapath
   const int wtiles = (Wo + TILE_M - 1) / TILE_M;
@@ -863,7 +874,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
   const int items = B * wtiles * hsegs;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->full[i], 128); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < G::NST; ++i) { umma::mbar_init(&bars->full[i], 128); umma::mbar_init(&bars->empty[i], 1); }
     umma::mbar_init(&bars->done, 1);
     umma::fence_mbar_init();
   }
@@ -879,8 +890,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
       const int h0 = hs * WG_ROWS, w0 = wt * TILE_M;
-      const uint32_t stage = n & 1;
-      umma::mbar_wait(&bars->empty[stage], ((n >> 1) & 1) ^ 1);
+      const uint32_t stage = n % G::NST;
+      umma::mbar_wait(&bars->empty[stage], ((n / G::NST) & 1) ^ 1);
       const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
       const uint32_t ds = xs + WG_X_BYTES;
       const __nv_bfloat16* ximg = x + (size_t)b * H * W * C;
@@ -906,8 +917,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
     uint32_t n = 0;
     uint32_t fresh = 1;     // accumulators not yet written
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const uint32_t stage = n & 1;
-      umma::mbar_wait(&bars->full[stage], (n >> 1) & 1);
+      const uint32_t stage = n % G::NST;
+      umma::mbar_wait(&bars->full[stage], (n / G::NST) & 1);
       umma::fence_proxy_async_smem();
       umma::tc_fence_after_sync();
       const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);

@@ -47,6 +47,24 @@ inline int tma_map_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// NHWC bf16 activation [B][H][W][32] seen as a 4-D tensor (channel, w, h, b) with a box of 8 channels x box_w pixels of one
+// row: a load at (8*cg, w0, h, b) lands as the [pixel][8 ch] plane of channel group cg that the SWIZZLE_NONE K-major UMMA
+// operands use, and every out-of-image pixel (w0 = -1, h = -1, h = H, the right edge) is zero-filled = the conv padding.
+inline int tma_map_nhwc_c8(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint32_t box_w) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc) return -1;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  const cuuint64_t dims[4] = {32, W, H, B};
+  const cuuint64_t strides[3] = {64, W * 64, H * W * 64};
+  const cuuint32_t box[4] = {8, box_w, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 // last failing encode, for error texts
 inline int tma_map_2d_checked(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
                               uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows, bool atom32, char* msg, size_t msg_len) {
