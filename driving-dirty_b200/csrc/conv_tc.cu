@@ -58,6 +58,19 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// one pixel's 32 channels (fp32 in registers) -> bf16 -> two 32-byte stores (64-byte aligned destination): whole sectors
+// per lane instead of four half-sector 16-byte stores
+__device__ __forceinline__ void store_pixel32(__nv_bfloat16* dst, const float (&v)[C]) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    pk[k] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  umma::stg256(dst, pk);
+  umma::stg256(dst + 16, pk + 8);
+}
+
 // One input row -> slab planes, by NT cooperating threads.  Thread (cg = ptid & 3, lp = ptid >> 2)
 // copies pixels lp, lp+NT/4, ...: source and destination advance by constants, only the bounds
 // predicate varies.  PPL > 0: stride-2 layout, odd pixels live PPL planes after the even ones.
@@ -252,13 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
               }
             }
           }
-#pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            float t8[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t8[k] = v[gq * 8 + k];
-            dd::st8<__nv_bfloat16>(out + off + gq * 8, t8);
-          }
+          store_pixel32(out + off, v);
         }
       }
     }
@@ -648,7 +655,7 @@ struct DgBars {
   uint32_t tmem_base;
 };
 
-__global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_constant__ CUtensorMap map_dy,
                                                                                const float* __restrict__ w_oihw,
                                                                                const __nv_bfloat16* __restrict__ mask,
                                                                                __nv_bfloat16* __restrict__ dx, int B,
@@ -672,7 +679,7 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __nv_bfloa
         __float2bfloat16_rn(w_oihw[(co * C + ci) * 9 + tap]);
   }
   if (tid == 0) {
-    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 32); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 4); }
     umma::fence_mbar_init();
   }
@@ -684,23 +691,24 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __nv_bfloa
   const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
   if (warp < NPROD) {
-    // =========================== producers: dy rows m0 .. m0+rows (slab g -> warp g % NPROD) ===
-    uint32_t g = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
-      const int m0 = hs * DG_MROWS;
-      const int rows = min(DG_MROWS, Hp - m0);
-      const int i0 = wt * TILE_M;
-      const __nv_bfloat16* img = dy + (size_t)b * Ho * Wo * C;
-      for (int s = 0; s <= rows; ++s, ++g) {
-        if ((g % NPROD) != (uint32_t)warp) continue;
-        const uint32_t slot = g % RING;
-        umma::mbar_wait(&bars->empty[slot], ((g / RING) & 1) ^ 1);
-        const int r = m0 + s;
-        const bool row_ok = r < Ho;
-        load_slab<129, 0, PS, 32>(umma::smem_u32(s_slab + slot * SLAB), img + (size_t)(row_ok ? r : 0) * Wo * C, row_ok,
-                                  i0, Wo, lane);
-        umma::cp_async_mbar_arrive_noinc(&bars->full[slot]);
+    // =========================== producer: dy rows m0 .. m0+rows, one thread, TMA ===============
+    // four [129 px][8 ch] boxes per dy row; rows >= Ho and columns >= Wo are zero-filled by the TMA unit
+    if (warp == 0 && lane == 0) {
+      umma::tma_prefetch_desc(&map_dy);
+      uint32_t g = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+        const int m0 = hs * DG_MROWS;
+        const int rows = min(DG_MROWS, Hp - m0);
+        const int i0 = wt * TILE_M;
+        for (int s = 0; s <= rows; ++s, ++g) {
+          const uint32_t slot = g % RING;
+          umma::mbar_wait(&bars->empty[slot], ((g / RING) & 1) ^ 1);
+          umma::mbar_expect_tx(&bars->full[slot], 4 * 129 * 16);
+          const uint32_t dst = umma::smem_u32(s_slab + slot * SLAB);
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) umma::tma_load_4d(dst + cg * PS, &map_dy, cg * 8, i0, m0 + s, b, &bars->full[slot]);
+        }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -719,8 +727,7 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __nv_bfloa
         const int rows = min(DG_MROWS, Hp - hs * DG_MROWS);
         for (int j = 0; j < rows; ++j, ++mctr) {
           const uint32_t need = g0 + j + 2;
-          for (; waited < need; ++waited) umma::mbar_wait(&bars->full[waited % RING], (waited / RING) & 1);
-          umma::fence_proxy_async_smem();
+          for (; waited < need; ++waited) umma::mbar_wait(&bars->full[waited % RING], (waited / RING) & 1);   // TMA writes: no proxy fence
           const uint32_t set = mctr & 1;
           umma::mbar_wait(&bars->acc_empty[set], ((mctr >> 1) & 1) ^ 1);
           umma::tc_fence_after_sync();
@@ -798,13 +805,7 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __nv_bfloa
                 }
               }
             }
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              float t8[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) t8[k] = v[gq * 8 + k];
-              dd::st8<__nv_bfloat16>(dx + off + gq * 8, t8);
-            }
+            store_pixel32(dx + off, v);
           }
         }
       }
@@ -858,7 +859,9 @@ struct WgBars {
 
 constexpr int WG_THREADS = 160;
 template <int STRIDE>
-__global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                       const __grid_constant__ CUtensorMap map_dy,
+                                                                       const __nv_bfloat16* __restrict__ x,
                                                                        const __nv_bfloat16* __restrict__ dy,
                                                                        float* __restrict__ partial, int B, int H,
                                                                        int W, int Ho, int Wo) {
@@ -874,7 +877,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
   const int items = B * wtiles * hsegs;
 
   if (tid == 0) {
-    for (int i = 0; i < G::NST; ++i) { umma::mbar_init(&bars->full[i], 128); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < G::NST; ++i) { umma::mbar_init(&bars->full[i], STRIDE == 1 ? 1 : 128); umma::mbar_init(&bars->empty[i], 1); }
     umma::mbar_init(&bars->done, 1);
     umma::fence_mbar_init();
   }
@@ -884,8 +887,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
   umma::tc_fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
-  if (warp < 4) {
-    // =========================== producers (warps 0..3) ========================================
+  if (warp < 4 && STRIDE == 1) {
+    // =========================== producer (stride 1): one thread, TMA ============================
+    // one [pixels][8 ch] box per (row, channel group) plane, rows / columns outside the image zero-filled (see the
+    // stride-1 forward kernel); 24 x boxes + 16 dy boxes per stage on one transaction barrier
+    if (tid == 0) {
+      umma::tma_prefetch_desc(&map_x);
+      umma::tma_prefetch_desc(&map_dy);
+      uint32_t n = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+        const int h0 = hs * WG_ROWS, w0 = wt * TILE_M;
+        const uint32_t stage = n % G::NST;
+        umma::mbar_wait(&bars->empty[stage], ((n / G::NST) & 1) ^ 1);
+        const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
+        const uint32_t ds = xs + WG_X_BYTES;
+        umma::mbar_expect_tx(&bars->full[stage], (uint32_t)(WG_XROWS * 4 * G::XPIX * 16 + WG_ROWS * 4 * TILE_M * 16));
+#pragma unroll 1
+        for (int r = 0; r < WG_XROWS; ++r)
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg)
+            umma::tma_load_4d(xs + (r * 4 + cg) * PS, &map_x, cg * 8, w0 - 1, h0 - 1 + r, b, &bars->full[stage]);
+#pragma unroll 1
+        for (int r = 0; r < WG_ROWS; ++r)
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg)
+            umma::tma_load_4d(ds + (r * 4 + cg) * PSD, &map_dy, cg * 8, w0, h0 + r, b, &bars->full[stage]);
+      }
+    }
+  } else if (warp < 4) {
+    // =========================== producers (stride 2: warps 0..3, cp.async) ======================
     uint32_t n = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
@@ -919,7 +950,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       const uint32_t stage = n % G::NST;
       umma::mbar_wait(&bars->full[stage], (n / G::NST) & 1);
-      umma::fence_proxy_async_smem();
+      if (STRIDE != 1) umma::fence_proxy_async_smem();     // cp.async writes (generic proxy); TMA writes need no fence
       umma::tc_fence_after_sync();
       const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
       const uint32_t x_lo = umma::desc_lo(xs, 128), d_lo = umma::desc_lo(xs + WG_X_BYTES, 128);
@@ -1190,13 +1221,10 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const float* 
         if (lane == 0) umma::mbar_arrive(&bars->acc_empty[buf]);
         if (wo < Wm) {
           __nv_bfloat16* dst = out + (((size_t)b * H + h0 + j) * Wm + wo) * C;
+          float v[C];
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            float t8[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t8[k] = fmaxf(__uint_as_float(r[gq * 8 + k]) + s_bias[gq * 8 + k], 0.f);
-            dd::st8<__nv_bfloat16>(dst + gq * 8, t8);
-          }
+          for (int k = 0; k < C; ++k) v[k] = fmaxf(__uint_as_float(r[k]) + s_bias[k], 0.f);
+          store_pixel32(dst, v);
         }
       }
     }
@@ -1407,8 +1435,12 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
     const int items = B * (((W + 1) / 2 + TILE_M - 1) / TILE_M) * (((H + 1) / 2 + DG_MROWS - 1) / DG_MROWS);
     cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_dgrad_s2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
     if (e != cudaSuccess) return fail((int)e, "dgrad_s2_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return fail(DD_ERR_ALIGNMENT, "dgrad_s2_tc: dy is not 16-byte aligned");
+    CUtensorMap mdy;
+    if (int r = tma_map_nhwc_c8(&mdy, in, (uint64_t)B, (uint64_t)Ho, (uint64_t)Wo, 129))
+      return fail(DD_ERR_UNSUPPORTED, "dgrad_s2_tc: cuTensorMapEncodeTiled -> %d", r);
     conv3x3_c32_dgrad_s2_tc_kernel<<<items < kSMs ? items : kSMs, NTHREADS, DG_SMEM, st>>>(
-        (const __nv_bfloat16*)in, w, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H, W, Ho, Wo);
+        mdy, w, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H, W, Ho, Wo);
     return check_launch("conv3x3_c32_dgrad_s2_tc");
   }
   return fail(DD_ERR_UNSUPPORTED, "conv_tc: mode %d stride %d", mode, stride);
@@ -1428,7 +1460,16 @@ static int wgrad_tc_launch(const void* x, const void* dy, float* dw, float* db, 
   auto k = conv3x3_c32_wgrad_tc_kernel<STRIDE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
   if (e != cudaSuccess) return fail((int)e, "wgrad_tc: cudaFuncSetAttribute(%d): %s", G::SMEM, cudaGetErrorString(e));
-  k<<<grid, WG_THREADS, G::SMEM, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, B, H, W, Ho, Wo);
+  CUtensorMap mx = {}, mdy = {};
+  if (STRIDE == 1) {
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0)
+      return fail(DD_ERR_ALIGNMENT, "tcgen05 wgrad: x / dy are not 16-byte aligned");
+    if (int r = tma_map_nhwc_c8(&mx, x, (uint64_t)B, (uint64_t)H, (uint64_t)W, G::XPIX))
+      return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: cuTensorMapEncodeTiled(x) -> %d", r);
+    if (int r = tma_map_nhwc_c8(&mdy, dy, (uint64_t)B, (uint64_t)Ho, (uint64_t)Wo, TILE_M))
+      return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: cuTensorMapEncodeTiled(dy) -> %d", r);
+  }
+  k<<<grid, WG_THREADS, G::SMEM, st>>>(mx, mdy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, B, H, W, Ho, Wo);
   if (int err = check_launch("conv3x3_c32_wgrad_tc")) return err;
   const long long npix = (long long)B * Ho * Wo;
   const int dbg = (int)((npix + 63) / 64 < kDbBlocks ? (npix + 63) / 64 : kDbBlocks);

@@ -8,7 +8,7 @@
 #include <vector>
 #include "../driving-dirty_b200/csrc/umma.cuh"
 
-template <int N, int NACC, int ASTEP, int TS>
+template <int N, int NACC, int ASTEP, int TS, int MN = 0>
 __global__ void __launch_bounds__(128) rate_kernel(long long* out, int trips) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -22,11 +22,12 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int trips) {
   umma::tc_fence_after_sync();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (warp == 0) {
-    constexpr uint32_t idesc = umma::make_idesc_bf16(128, N, false, false);
+    constexpr uint32_t idesc = umma::make_idesc_bf16(128, N, MN != 0, MN != 0);
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
     const uint32_t sa = __shfl_sync(0xffffffffu, umma::smem_u32(smem), 0);
-    const uint32_t a_lo = umma::desc_lo(sa, 2176), b_lo = umma::desc_lo(sa + 40 * 1024, 512);
-    constexpr uint32_t hi = umma::desc_hi(128);
+    // MN-major (both operands, as in the weight-gradient kernels): LBO = 128 between the 8-row K groups, SBO = plane stride
+    const uint32_t a_lo = umma::desc_lo(sa, MN ? 128 : 2176), b_lo = umma::desc_lo(sa + 40 * 1024, MN ? 128 : 512);
+    constexpr uint32_t hi = umma::desc_hi(MN ? 2176 : 128);
     const long long t0 = clock64();
     if (umma::elect_one()) {
       for (int t = 0; t < trips; ++t) {
@@ -59,11 +60,11 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int trips) {
   if (threadIdx.x < 32) umma::tmem_dealloc(tbase, 512);
 }
 
-template <int N, int NACC, int ASTEP, int TS>
+template <int N, int NACC, int ASTEP, int TS, int MN = 0>
 void run(const char* name, long long* d) {
   const int trips = 256, grid = 148, nmma = trips * 16;
-  cudaFuncSetAttribute(rate_kernel<N, NACC, ASTEP, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 1024);
-  rate_kernel<N, NACC, ASTEP, TS><<<grid, 128, 64 * 1024 + 1024>>>(d, trips);
+  cudaFuncSetAttribute(rate_kernel<N, NACC, ASTEP, TS, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 1024);
+  rate_kernel<N, NACC, ASTEP, TS, MN><<<grid, 128, 64 * 1024 + 1024>>>(d, trips);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%-56s CUDA error %s\n", name, cudaGetErrorString(e)); return; }
   std::vector<long long> h(grid * 2);
@@ -95,6 +96,8 @@ int main() {
   run<160, 1, 16, 0>("SS N=160 1 accumulator", d);
   run<192, 1, 16, 0>("SS N=192 1 accumulator", d);
   run<224, 1, 16, 0>("SS N=224 1 accumulator", d);
+  run<32, 1, 256, 0, 1>("SS MN-major A and B, N=32", d);
+  run<64, 1, 256, 0, 1>("SS MN-major A and B, N=64 (c2 weight gradient)", d);
   run<32, 1, 16, 1>("TS (A in TMEM) N=32 1 accumulator", d);
   run<32, 4, 16, 1>("TS (A in TMEM) N=32 4 accumulators", d);
   run<64, 4, 16, 1>("TS (A in TMEM) N=64 4 accumulators", d);
