@@ -863,13 +863,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
                                                                        const __grid_constant__ CUtensorMap map_dy,
                                                                        const __nv_bfloat16* __restrict__ x,
                                                                        const __nv_bfloat16* __restrict__ dy,
-                                                                       float* __restrict__ partial, int B, int H,
+                                                                       float* __restrict__ partial, float* __restrict__ db_partial, int B, int H,
                                                                        int W, int Ho, int Wo) {
   using G = WgGeo<STRIDE>;
   constexpr int WG_ROWS = G::ROWS, WG_XROWS = G::XROWS, WG_X_BYTES = G::X_BYTES, WG_STAGE_BYTES = G::STAGE_BYTES;
   constexpr int WG_PARTIAL = G::PARTIAL;
   extern __shared__ __align__(1024) uint8_t smem[];
   WgBars* bars = reinterpret_cast<WgBars*>(smem + G::NST * WG_STAGE_BYTES);
+  __shared__ float s_db[2][C];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role code stays on the uniform datapath
   const int wtiles = (Wo + TILE_M - 1) / TILE_M;
@@ -877,7 +878,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
   const int items = B * wtiles * hsegs;
 
   if (tid == 0) {
-    for (int i = 0; i < G::NST; ++i) { umma::mbar_init(&bars->full[i], STRIDE == 1 ? 1 : 128); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < G::NST; ++i) { umma::mbar_init(&bars->full[i], STRIDE == 1 ? 1 : 128); umma::mbar_init(&bars->empty[i], STRIDE == 1 ? 3 : 1); }
     umma::mbar_init(&bars->done, 1);
     umma::fence_mbar_init();
   }
@@ -913,6 +914,44 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
 #pragma unroll
           for (int cg = 0; cg < 4; ++cg)
             umma::tma_load_4d(ds + (r * 4 + cg) * PSD, &map_dy, cg * 8, w0, h0 + r, b, &bars->full[stage]);
+      }
+    } else if (warp == 1 || warp == 2) {
+      // =========================== bias gradient (stride 1): db[co] = sum of dy over pixels ========
+      // The dy planes are in shared memory anyway: two otherwise idle warps add them up per stage (thread = pixel
+      // column, 32 fp32 accumulators = one per channel), instead of a separate kernel reading dy from HBM again.
+      float acc[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k) acc[k] = 0.f;
+      const int px0 = (warp - 1) * 32 + lane;              // pixels px0 and px0 + 64 of the strip
+      uint32_t n = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const uint32_t stage = n % G::NST;
+        umma::mbar_wait(&bars->full[stage], (n / G::NST) & 1);
+        const uint32_t ds = umma::smem_u32(smem + stage * WG_STAGE_BYTES) + WG_X_BYTES;
+#pragma unroll
+        for (int pl = 0; pl < WG_ROWS * 4; ++pl) {           // plane = (dy row, channel group)
+#pragma unroll
+          for (int hpx = 0; hpx < 2; ++hpx) {
+            uint32_t q0, q1, q2, q3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3)
+                         : "r"(ds + pl * PSD + (px0 + 64 * hpx) * 16));
+            const uint32_t qq[4] = {q0, q1, q2, q3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[k]));
+              acc[(pl & 3) * 8 + 2 * k] += f.x;
+              acc[(pl & 3) * 8 + 2 * k + 1] += f.y;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bars->empty[stage]);
+      }
+#pragma unroll
+      for (int k = 0; k < C; ++k) acc[k] = dd::warp_sum(acc[k]);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) s_db[warp - 1][k] = acc[k];
       }
     }
   } else if (warp < 4) {
@@ -1003,6 +1042,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(con
   }
   umma::tc_fence_before_sync();
   __syncthreads();
+  if (STRIDE == 1 && tid < C) db_partial[(size_t)blockIdx.x * C + tid] = s_db[0][tid] + s_db[1][tid];
   if (warp == 4) umma::tmem_dealloc(tmem, 256);
 }
 
@@ -1469,12 +1509,15 @@ static int wgrad_tc_launch(const void* x, const void* dy, float* dw, float* db, 
     if (int r = tma_map_nhwc_c8(&mdy, dy, (uint64_t)B, (uint64_t)Ho, (uint64_t)Wo, TILE_M))
       return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: cuTensorMapEncodeTiled(dy) -> %d", r);
   }
-  k<<<grid, WG_THREADS, G::SMEM, st>>>(mx, mdy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, B, H, W, Ho, Wo);
+  k<<<grid, WG_THREADS, G::SMEM, st>>>(mx, mdy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, dbp, B, H, W, Ho, Wo);
   if (int err = check_launch("conv3x3_c32_wgrad_tc")) return err;
-  const long long npix = (long long)B * Ho * Wo;
-  const int dbg = (int)((npix + 63) / 64 < kDbBlocks ? (npix + 63) / 64 : kDbBlocks);
-  colsum_nhwc_bf16_kernel<<<dbg, 256, 0, st>>>((const __nv_bfloat16*)dy, npix, dbp);
-  if (int err = check_launch("colsum_nhwc_bf16")) return err;
+  int dbg = grid;                       // stride 1: the weight-gradient kernel wrote one db partial per CTA
+  if (STRIDE != 1) {
+    const long long npix = (long long)B * Ho * Wo;
+    dbg = (int)((npix + 63) / 64 < kDbBlocks ? (npix + 63) / 64 : kDbBlocks);
+    colsum_nhwc_bf16_kernel<<<dbg, 256, 0, st>>>((const __nv_bfloat16*)dy, npix, dbp);
+    if (int err = check_launch("colsum_nhwc_bf16")) return err;
+  }
   wgrad_tc_reduce_kernel<<<(9 * C * C + C + 255) / 256, 256, 0, st>>>(partial, grid * G::NQ, dbp, dbg, dw, db);
   return check_launch("wgrad_tc_reduce");
 }
