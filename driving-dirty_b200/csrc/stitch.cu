@@ -21,16 +21,30 @@ __global__ void __launch_bounds__(256) stitch_rows_kernel(const float* __restric
     const int b = row / (3 * H);
     const float* vbase = views + (size_t)b * 6 * view_elems + ((size_t)c * H + h) * W;
     float2* orow = reinterpret_cast<float2*>(mosaic + (size_t)row * 6 * W);
-    for (int i = threadIdx.x; i < pairs; i += blockDim.x) {
-      const int j = i / W2;
-      const int w2 = i - j * W2;
-      const float2* src = reinterpret_cast<const float2*>(vbase + (size_t)dd::view_of_slot(j) * view_elems);
-      float2 v = __ldg(src + w2);
-      if (MODE == 1 && j == slot) {
-        reinterpret_cast<float2*>(y + (size_t)row * W)[w2] = v;
-        v = make_float2(0.f, 0.f);
+    // four independent 8-byte pairs per lane and trip, all loads issued before the first store: 8 KB in flight per CTA
+    for (int i0 = threadIdx.x; i0 < pairs; i0 += 4 * blockDim.x) {
+      float2 v[4];
+      int jj[4], ww[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < pairs) {
+          jj[u] = i / W2;
+          ww[u] = i - jj[u] * W2;
+          v[u] = __ldcs(reinterpret_cast<const float2*>(vbase + (size_t)dd::view_of_slot(jj[u]) * view_elems) + ww[u]);
+        }
       }
-      orow[i] = v;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < pairs) {
+          if (MODE == 1 && jj[u] == slot) {
+            reinterpret_cast<float2*>(y + (size_t)row * W)[ww[u]] = v[u];
+            v[u] = make_float2(0.f, 0.f);
+          }
+          __stcs(orow + i, v[u]);
+        }
+      }
     }
   }
 }
