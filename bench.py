@@ -172,8 +172,11 @@ def time_kernel(fn, iters=5):
 
 
 def dominant_kernel_roofline(batch: int, dtype: torch.dtype, pk, pk_src):
-    """Times the c2-shaped conv kernels (32->32 3x3 over the 256x1836 mosaic: fwd, dgrad, wgrad)
-    alone on the current stream with CUDA events and reports the slowest against the bf16 peak."""
+    """Times the c2-shaped conv kernels (32->32 3x3 over the 256x1836 mosaic: fwd, dgrad, wgrad) alone on the
+    current stream with CUDA events.  Unfused, such a conv moves 128 B per pixel for 18,432 flop (144 flop/B, below
+    this box's ridge of 243 flop/B), so the roof that bounds it is HBM: `roofline` reports the slowest of the three
+    against the measured copy bandwidth, with ALGORITHMIC bytes per launch (activations in + out; dgrad also reads the
+    ReLU mask) -- and the bf16 tensor fractions the north star asks about ride along in `all`."""
     from driving_dirty_b200 import _lib
     from driving_dirty_b200._lib import call, dtype_code, stream_ptr
     dev = torch.device("cuda")
@@ -188,24 +191,36 @@ def dominant_kernel_roofline(batch: int, dtype: torch.dtype, pk, pk_src):
     n = int(_lib.load().dd_conv_wgrad_workspace_bytes())
     ws = torch.empty(n, dtype=torch.uint8, device=dev)
     st = stream_ptr()
+    act = x.numel() * x.element_size()
     kernels = {
-        "conv3x3_c32 fwd (c2)": lambda: call("dd_conv3x3_c32_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(),
-                                             out.data_ptr(), code, batch, H, W, 1, 0, st),
-        "conv3x3_c32 dgrad (c2)": lambda: call("dd_conv3x3_c32_dgrad", dy.data_ptr(), w.data_ptr(), x.data_ptr(),
-                                               out.data_ptr(), code, batch, H, W, 1, 0, st),
-        "conv3x3_c32 wgrad (c2)": lambda: call("dd_conv3x3_c32_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
-                                               db.data_ptr(), ws.data_ptr(), n, code, batch, H, W, 1, 0, st),
+        "conv3x3_c32 fwd (c2)": (lambda: call("dd_conv3x3_c32_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                              out.data_ptr(), code, batch, H, W, 1, 0, st), 2 * act),
+        "conv3x3_c32 dgrad (c2)": (lambda: call("dd_conv3x3_c32_dgrad", dy.data_ptr(), w.data_ptr(), x.data_ptr(),
+                                                out.data_ptr(), code, batch, H, W, 1, 0, st), 3 * act),
+        "conv3x3_c32 wgrad (c2)": (lambda: call("dd_conv3x3_c32_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                                                db.data_ptr(), ws.data_ptr(), n, code, batch, H, W, 1, 0, st), 2 * act),
     }
+    traffic = {}
+    try:        # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture of these kernels
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
     flops = FLOP_C2_PER_SCENE * batch
     rows = []
-    for name, fn in kernels.items():
+    for name, (fn, nbytes) in kernels.items():
         t = time_kernel(fn)
-        rows.append({"kernel": name, "ms": t * 1e3, "tflops": flops / t / 1e12})
+        rows.append({"kernel": name, "ms": t * 1e3, "gbs": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / pk["hbm_gbs"],
+                     "algorithmic_bytes_per_launch": nbytes, "tflops": flops / t / 1e12,
+                     "tensor_frac": flops / t / 1e12 / pk["bf16_tflops"],
+                     "dram_bytes_per_launch_ncu": traffic.get(name) if batch == 32 else None})
     worst = max(rows, key=lambda r: r["ms"])
-    peak = pk["bf16_tflops"]
-    roof = {"bound": "tensor", "kernel": worst["kernel"], "achieved": worst["tflops"], "peak": peak,
-            "unit": "TFLOP/s", "frac": worst["tflops"] / peak, "traffic": None, "peak_source": pk_src + ", burst",
-            "algorithmic_flops_per_launch": flops, "ms_per_launch": worst["ms"], "all": rows}
+    roof = {"bound": "hbm", "kernel": worst["kernel"], "achieved": worst["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": worst["hbm_frac"], "traffic": worst["dram_bytes_per_launch_ncu"],
+            "peak_source": pk_src + " (copy bandwidth; bf16 peak for tensor_frac: burst)",
+            "algorithmic_bytes_per_launch": worst["algorithmic_bytes_per_launch"],
+            "algorithmic_flops_per_launch": flops, "ms_per_launch": worst["ms"],
+            "why_hbm": "unfused 32->32 3x3 conv in bf16 NHWC: 144 flop/B < ridge 243 flop/B", "all": rows}
     del x, dy, out
     torch.cuda.empty_cache()
     return roof
@@ -224,6 +239,10 @@ def hbm_kernel_rooflines(batch: int, pk):
     t = time_kernel(lambda: ops.bce_threat(logits, target, want_probs=False, want_binary=False))
     nbytes = 2 * logits.numel() * 4
     rows.append({"kernel": "bce+ts fwd (f32 target, sums only)", "ms": t * 1e3, "gbs": nbytes / t / 1e9,
+                 "frac": nbytes / t / 1e9 / pk["hbm_gbs"]})
+    t = time_kernel(lambda: ops.bce_threat(logits, target, want_probs=True, want_binary=True))
+    nbytes = logits.numel() * 13          # logits + target + probs (f32) + binary map (u8)
+    rows.append({"kernel": "bce+ts fwd (f32 target) + probs + binary map", "ms": t * 1e3, "gbs": nbytes / t / 1e9,
                  "frac": nbytes / t / 1e9 / pk["hbm_gbs"]})
     return rows
 
