@@ -58,30 +58,52 @@ def peaks():
 
 
 class ClockSampler:
+    """nvidia-smi polled every 20 ms by a reader thread.  start() returns once the first sample has arrived (nvidia-smi
+    takes ~1 s to come up, longer than the whole timed region); mark() / stop() bracket the timed region, and only the
+    samples taken inside it are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.proc = None
+        import threading
+        self.proc, self.lines, self.t0 = None, [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except Exception:  # noqa: BLE001
             self.proc = None
+            return
+
+        def reader():
+            for line in self.proc.stdout:
+                self.lines.append((time.perf_counter(), line))
+
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+        deadline = time.perf_counter() + 10.0
+        while not self.lines and time.perf_counter() < deadline:
+            time.sleep(0.01)
+
+    def mark(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
+        t1 = time.perf_counter()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)                      # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-            out = ""
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.03]
+        used = inside if inside else [l for (_, l) in self.lines[-3:]]
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+        for line in used:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
@@ -93,7 +115,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_in_timed_region": len(inside),
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,8 +182,9 @@ def build_model(dtype: str, device):
     return model
 
 
-def time_kernel(fn, iters=5):
-    fn()
+def time_kernel(fn, iters=20):
+    for _ in range(3):
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -286,11 +310,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None      # up and polling before the GPU work starts
     # >= 5 untimed steps: the first ones map the symmetric / multicast buffers and size the allocator's pools
     for _ in range(max(args.warmup, 5)):
         step(views_d, road_d)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
