@@ -121,8 +121,10 @@ class FusedAdam(torch.optim.Optimizer):
             lo, hi = shard_bounds(small_total, self.world, self.rank)
             self._flat = dict(off=flat_off, lo=lo, hi=hi, channel=0, params=small, grad_views=views, key="flat")
         # per NVLink direction and GPU the multicast form moves n(1 + 1/N) bytes (the switch also loops the own replica
-        # back), peer loads / stores 2n(N-1)/N: multicast wins from N = 3 on (measured at N = 2: 3.5 ms vs 2.1 ms)
-        want_mc = (self.world > 2) if multicast is None else bool(multicast)
+        # back), peer loads / stores 2n(N-1)/N, at a somewhat lower achieved link rate for multimem.  Measured per step
+        # (profiles/r1_step_times_n8.txt and the N = 2 / N = 4 runs): N = 2: 3.5 vs 2.1 ms for the update alone;
+        # N = 4: 8.56 vs 7.9-8.2 ms per training step; N = 8: 8.68 vs 8.8 ms.  Multicast from N = 6 on.
+        want_mc = (self.world >= 6) if multicast is None else bool(multicast)
         mc = int(hdl.multicast_ptr) if (want_mc and hdl.has_multicast_support) else 0
         if multicast is True and mc == 0:
             raise RuntimeError("FusedAdam: multicast requested but the symmetric buffer has no multicast mapping")
