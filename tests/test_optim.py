@@ -116,3 +116,13 @@ def test_fused_adam_sharded_two_gpus(tmp_path, multicast, overlap):
     mp.spawn(_sharded_worker, args=(2, _free_port(), multicast, overlap, out), nprocs=2, join=True)
     ew, eb, same = open(out).read().split()
     assert float(ew) < 5e-6 and float(eb) < 5e-6 and same == "1", (ew, eb, same)
+
+
+def test_flat_layout_is_aligned_and_disjoint():
+    from driving_dirty_b200.optim import flat_layout
+    numels = [640000, 256, 65536, 7, 864, 9216, 32, 1]
+    offs, total = flat_layout(numels)
+    assert offs[0] == 0 and all(o % 64 == 0 for o in offs) and total % 64 == 0
+    for (o, n), o_next in zip(zip(offs, numels), offs[1:] + [total]):
+        assert o + n <= o_next
+    assert total % 4 == 0          # shard_bounds works on 16-byte granules
