@@ -71,7 +71,11 @@ int dd_conv_c1_wgrad(const float* in, int in_is_views, const void* dy, int dtype
                      void* stream);
 
 /* c2 / c3: 32->32, 3x3, pad 1, stride 1 or 2, + bias + ReLU; NHWC in [B,H,W,32] ->
- * NHWC out [B,Ho,Wo,32], Ho = (H-1)/stride+1. */
+ * NHWC out [B,Ho,Wo,32], Ho = (H-1)/stride+1.  The bf16 tensor-core kernels read their activations
+ * through TMA tensor maps built per call from the pointer and shape (nothing is cached): `in` / `dy`
+ * / `x` must be 16-byte aligned and densely packed (DD_ERR_ALIGNMENT otherwise); outputs and the
+ * ReLU-mask input are accessed in 32-byte pieces per pixel (64-byte pixels of a torch allocation
+ * are always aligned). */
 int dd_conv3x3_c32_fwd(const void* in, const float* w_oihw, const float* bias, void* out,
                        int dtype, int B, int H, int W, int stride, int impl, void* stream);
 /* dx [B,H,W,32] = conv_transpose(dy, w) * (x > 0)   (x = this layer's input = previous
