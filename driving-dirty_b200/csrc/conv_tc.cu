@@ -1465,6 +1465,9 @@ bool conv_tc_supported(int H, int W, int stride, int mode) {
 
 int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int stride,
                        int mode, const void* mask, cudaStream_t st) {
+  // the epilogues store (and read the ReLU mask) in 32-byte pieces; the producers read 16-byte pieces
+  if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask)) & 31) != 0 || (reinterpret_cast<uintptr_t>(in) & 15) != 0)
+    return fail(DD_ERR_ALIGNMENT, "conv_tc: activations must be 32-byte aligned (in %p, out %p, mask %p)", in, out, mask);
   static const bool old_s1 = getenv("DD_CONV_OLD_S1") != nullptr;   // A/B timing aid: the 18 x N=32 gather kernel
   if (mode == 0 && stride == 1) return old_s1 ? launch<1, 0>(in, w, bias, nullptr, out, B, H, W, st) : launch_s1<0>(in, w, bias, nullptr, out, B, H, W, st);
   if (mode == 0 && stride == 2) return launch<2, 0>(in, w, bias, nullptr, out, B, H, W, st);
@@ -1524,6 +1527,7 @@ static int wgrad_tc_launch(const void* x, const void* dy, float* dw, float* db, 
 
 int conv_c1_fwd_tc(const float* in, int in_is_views, const float* w, const float* bias, void* out, int B, int H, int Wm,
                    cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(out) & 31) != 0) return fail(DD_ERR_ALIGNMENT, "conv_c1_tc: out %p is not 32-byte aligned", out);
   const int items = B * ((Wm + TILE_M - 1) / TILE_M) * ((H + ROWS - 1) / ROWS);
   const int grid = items < kSMs ? items : kSMs;
   auto launch1 = [&](auto k) {
