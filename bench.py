@@ -5,7 +5,8 @@ bf16 activations, batch 32 scenes per GPU, views 6x3x256x306, hidden 256 / laten
     python bench.py [--gpus N --steps K --warmup W] [--impl reference]
 
 One "step" = zero_grad + stitch/conv encoder/dense blocks/800x800 head + fused BCE/threat score +
-backward + (N>1: gradient all-reduce) + Adam, on one batch of synthetic scenes.  `value` is timed
+backward + Adam on one batch of synthetic scenes; for N>1 the gradient exchange, the Adam update of each rank's
+shard and the all-gather of the new weights are one kernel over NVLink peer memory (optim.FusedAdam).  `value` is timed
 on the device with inputs resident in HBM; `e2e` goes through the reference-facing module call with
 HOST (pinned) input buffers, H2D copies and a D2H read of the loss inside the timed region.
 `--impl reference` times the CPU port of the reference path (oracle/scene_oracle.py: the same torch
