@@ -76,14 +76,35 @@ class FusedAdam(torch.optim.Optimizer):
         self._lib = _lib.load()     # raises when the CUDA library is missing: no fallback
         for g in self.param_groups:
             for p in g["params"]:
-                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                    raise RuntimeError("FusedAdam: parameters must be contiguous fp32 CUDA tensors")
+                self._check_param(p)
         if self.world > 1:
             self._setup_sharding(shard_min_numel, multicast, broadcast_init)
 
+    # The two places where the device is touched outside `_launch_sharded`; tests/test_optim.py overrides them (and the
+    # launch) to run the sharding logic itself under gloo on CPU tensors.
+    def _check_param(self, p):
+        if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+            raise RuntimeError("FusedAdam: parameters must be contiguous fp32 CUDA tensors")
+
+    def _alloc_symmetric(self, numel, device, multicast):
+        """One symmetric-memory buffer of `numel` floats per rank -> (buffer, handle with .barrier(channel=),
+        per-rank device pointers, multicast address or 0)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(buf, grp)
+        # per NVLink direction and GPU the multicast form moves n(1 + 1/N) bytes (the switch also loops the own replica
+        # back), peer loads / stores 2n(N-1)/N, at a somewhat lower achieved link rate for multimem.  Measured per step
+        # (profiles/r1_step_times_n8.txt and the N = 2 / N = 4 runs): N = 2: 3.5 vs 2.1 ms for the update alone;
+        # N = 4: 8.56 vs 7.9-8.2 ms per training step; N = 8: 8.68 vs 8.8 ms.  Multicast from N = 6 on.
+        want_mc = (self.world >= 6) if multicast is None else bool(multicast)
+        mc = int(hdl.multicast_ptr) if (want_mc and hdl.has_multicast_support) else 0
+        if multicast is True and mc == 0:
+            raise RuntimeError("FusedAdam: multicast requested but the symmetric buffer has no multicast mapping")
+        return buf, hdl, [int(x) for x in hdl.buffer_ptrs], mc
+
     # ------------------------------------------------------------------------------------------
     def _setup_sharding(self, shard_min_numel, multicast, broadcast_init):
-        import torch.distributed._symmetric_memory as symm_mem
         params = [p for g in self.param_groups for p in g["params"]]
         if broadcast_init:          # replicas must start identical (Lightning ddp broadcasts rank 0's weights)
             src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
@@ -97,9 +118,7 @@ class FusedAdam(torch.optim.Optimizer):
         if total == 0:
             return
         dev = params[0].device
-        buf = symm_mem.empty(2 * total, dtype=torch.float32, device=dev)      # [gradients | weights]
-        grp = self.group if self.group is not None else dist.group.WORLD
-        hdl = symm_mem.rendezvous(buf, grp)
+        buf, hdl, ptrs, mc = self._alloc_symmetric(2 * total, dev, multicast)      # [gradients | weights]
         buf.zero_()
 
         def adopt(p, off):
@@ -115,23 +134,16 @@ class FusedAdam(torch.optim.Optimizer):
             p._dd_grad_buffer = gview                    # ops.linear's weight-gradient kernel writes here ...
             p._dd_grad_ready = (lambda q: (lambda: self._on_grad_written(q)))(p)     # ... and then calls this
             lo, hi = shard_bounds(p.numel(), self.world, self.rank)
-            self._regions[id(p)] = dict(off=off, lo=lo, hi=hi, channel=1 + len(self._regions), key=p)
+            self._regions[id(p)] = dict(off=off, n=p.numel(), lo=lo, hi=hi, channel=1 + len(self._regions), key=p)
         if small:
             views = [adopt(p, flat_off + o) for p, o in zip(small, small_offs)]
             lo, hi = shard_bounds(small_total, self.world, self.rank)
-            self._flat = dict(off=flat_off, lo=lo, hi=hi, channel=0, params=small, grad_views=views, key="flat")
-        # per NVLink direction and GPU the multicast form moves n(1 + 1/N) bytes (the switch also loops the own replica
-        # back), peer loads / stores 2n(N-1)/N, at a somewhat lower achieved link rate for multimem.  Measured per step
-        # (profiles/r1_step_times_n8.txt and the N = 2 / N = 4 runs): N = 2: 3.5 vs 2.1 ms for the update alone;
-        # N = 4: 8.56 vs 7.9-8.2 ms per training step; N = 8: 8.68 vs 8.8 ms.  Multicast from N = 6 on.
-        want_mc = (self.world >= 6) if multicast is None else bool(multicast)
-        mc = int(hdl.multicast_ptr) if (want_mc and hdl.has_multicast_support) else 0
-        if multicast is True and mc == 0:
-            raise RuntimeError("FusedAdam: multicast requested but the symmetric buffer has no multicast mapping")
-        self._symm = dict(buf=buf, hdl=hdl, total=total, ptrs=[int(x) for x in hdl.buffer_ptrs], mc=mc)
+            self._flat = dict(off=flat_off, n=small_total, lo=lo, hi=hi, channel=0, params=small, grad_views=views, key="flat")
+        self._symm = dict(buf=buf, hdl=hdl, total=total, ptrs=ptrs, mc=mc)
         if self._overlap:
             self._side = torch.cuda.Stream(device=dev)
-        torch.cuda.synchronize()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         hdl.barrier()
 
     @property
