@@ -20,7 +20,7 @@ traffic per GPU, and no NCCL kernel in the step.
 
 Semantics are torch.optim.Adam's (amsgrad off, L2 weight decay); ``param_groups[i]['lr']`` is read
 every step, so ``ReduceLROnPlateau`` (roadmap_bce_v2.py:156) works unchanged; tensors whose
-gradient is ``None`` are skipped.
+gradient is ``None`` are skipped (a partly frozen flat bucket is updated per tensor on every replica).
 """
 from __future__ import annotations
 
@@ -73,6 +73,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._side = None           # stream of the updates launched from the backward pass
         self._written = set()       # ids of wide params whose gradient replica was written since the last step()
         self._launched = set()      # ... and whose update is already running on the side stream
+        self._flat_replicated = False   # the flat bucket fell back to per-tensor replicated updates (partly frozen model)
         self._lib = _lib.load()     # raises when the CUDA library is missing: no fallback
         for g in self.param_groups:
             for p in g["params"]:
@@ -183,19 +184,10 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         if self.world == 1:
-            st_ptr = stream_ptr()
             for g in self.param_groups:
                 for p in g["params"]:
-                    if p.grad is None:
-                        continue
-                    grad = p.grad
-                    if not (grad.is_contiguous() and grad.dtype == torch.float32):
-                        grad = grad.contiguous().float()
-                    st = self._state(p, p.numel(), p.device)
-                    st["step"] += 1
-                    call("dd_adam_step", p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                         p.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                         float(g["weight_decay"]), st["step"], 1.0, st_ptr)
+                    if p.grad is not None:
+                        self._launch_local(g, p, p.grad)
             return loss
         if self._symm is None:
             return loss
@@ -204,11 +196,26 @@ class FusedAdam(torch.optim.Optimizer):
         fl = self._flat
         if fl is not None:
             have = [p.grad is not None for p in fl["params"]]
-            if any(have):
-                if not all(have):
-                    # torch.optim.Adam skips tensors without a gradient; one bucket = one step counter, so a partly
-                    # frozen bucket has no faithful sharded form
-                    raise NotImplementedError("FusedAdam (world > 1): every tensor of the flat bucket needs a gradient, or none")
+            if any(have) and (self._flat_replicated or not all(have)):
+                # A partly frozen bucket (e.g. RoadMapBCE before unfreeze_epoch_no, roadmap_bce_v2.py:127-129):
+                # torch.optim.Adam skips tensors without a gradient and keeps a step count per tensor, which one sharded
+                # bucket cannot express.  These tensors are 0.1 % of the bytes: average each present gradient with an
+                # all-reduce and update every replica locally, per tensor -- and stay in this form from then on, so the
+                # per-tensor moments remain the truth.
+                if self.state.get("flat"):
+                    raise NotImplementedError("FusedAdam (world > 1): the flat bucket was already stepped in its sharded form; "
+                                              "freeze parameters before the first step, not after")
+                self._flat_replicated = True
+                nccl = dist.get_backend(self.group) == "nccl"
+                g = self.param_groups[0]
+                for p in fl["params"]:
+                    if p.grad is None:
+                        continue
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, group=self.group)
+                    if not nccl:
+                        p.grad.div_(self.world)
+                    self._launch_local(g, p, p.grad)
+            elif all(have):
                 torch._foreach_copy_(fl["grad_views"], [p.grad for p in fl["params"]])
                 todo.append(fl)
         if todo:
@@ -221,6 +228,16 @@ class FusedAdam(torch.optim.Optimizer):
         self._launched.clear()
         self._written.clear()
         return loss
+
+    def _launch_local(self, g, p, grad):
+        """One dd_adam_step launch: the whole tensor, this replica only."""
+        if not (grad.is_contiguous() and grad.dtype == torch.float32):
+            grad = grad.contiguous().float()
+        st = self._state(p, p.numel(), p.device)
+        st["step"] += 1
+        call("dd_adam_step", p.data_ptr(), grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+             p.numel(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+             float(g["weight_decay"]), st["step"], 1.0, stream_ptr())
 
     def _launch_sharded(self, r, ctas_per_sm):
         sy, W = self._symm, self.world

@@ -93,6 +93,16 @@ def _adam_worker(rank, world, port, q):
                 lo_k, hi_k = shard_bounds(r["n"], self.world, rk)
                 dist.broadcast(buf[total + off + lo_k: total + off + hi_k], src=rk)
 
+        def _launch_local(self, g, p, grad):
+            st = self._state(p, p.numel(), p.device)
+            st["step"] += 1
+            lr, b1, b2, eps, wd = self._hyper()
+            gr = grad + wd * p.data if wd else grad
+            st["exp_avg"].lerp_(gr.reshape(-1), 1 - b1)
+            st["exp_avg_sq"].mul_(b2).addcmul_(gr.reshape(-1), gr.reshape(-1), value=1 - b2)
+            bc1, bc2 = 1 - b1 ** st["step"], 1 - b2 ** st["step"]
+            p.data.sub_(((lr / bc1) * st["exp_avg"] / (st["exp_avg_sq"].sqrt() / bc2 ** 0.5 + eps)).view_as(p))
+
     g = torch.Generator().manual_seed(3)
     shapes = [(64, 66), (7,), (3, 5), (130,)]                 # 4224 elements: sharded on its own; the rest: flat bucket
     init = [torch.randn(s, generator=g) for s in shapes]
@@ -122,7 +132,25 @@ def _adam_worker(rank, world, port, q):
         refused = False
     except RuntimeError:
         refused = True
-    q.put((rank, err < 1e-6 and refused, err))
+    opt.step()
+    # ---- a partly frozen flat bucket (RoadMapBCE before unfreeze_epoch_no): per-tensor replicated updates, torch's skip rule
+    params2 = [torch.nn.Parameter(t.clone()) for t in init]
+    opt2 = GlooAdam(params2, lr=1e-2, shard_min_numel=1024)
+    ref2 = [t.clone().requires_grad_(True) for t in init]
+    ropt2 = torch.optim.Adam(ref2, lr=1e-2)
+    for step in range(3):
+        frozen = {3} if step < 2 else set()                    # tensor 3 gets its first gradient at the third step
+        opt2.zero_grad()
+        params2[0]._dd_grad_buffer.copy_(grads[step][rank][0])
+        params2[0]._dd_grad_ready()
+        for i in (1, 2, 3):
+            params2[i].grad = None if i in frozen else grads[step][rank][i].clone()
+            ref2[i].grad = None if i in frozen else sum(grads[step][r][i] for r in range(world)) / world
+        ref2[0].grad = sum(grads[step][r][0] for r in range(world)) / world
+        opt2.step()
+        ropt2.step()
+    err2 = max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(params2, ref2))
+    q.put((rank, err < 1e-6 and refused and err2 < 1e-6 and opt2._flat_replicated, (err, err2)))
     dist.destroy_process_group()
 
 
