@@ -109,9 +109,14 @@ class ClockSampler:
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                sm_v, mx_v = float(f[0]), float(f[1])
             except ValueError:
                 continue
+            sm.append(sm_v); mx.append(mx_v)
+            try:
+                pw.append(float(f[2]))          # "[N/A]" on boxes that do not report power
+            except ValueError:
+                pass
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
