@@ -10,7 +10,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxBlocks = dd::kSMs * 8;
-constexpr int kSlots = 6;  // bce, sum_p, sum_tp, n_t, n_r, n_tr
+constexpr int kSlots = 8;  // bce, sum_p, sum_tp, n_t, n_r, n_tr, sum_t, sum_t*r
 
 struct Workspace {
   double partial[kMaxBlocks][kSlots];
@@ -23,7 +23,7 @@ struct Workspace {
 __device__ __forceinline__ bool binarise(float x) { return x > __uint_as_float(0x33C00000u); }
 
 struct Acc {
-  float bce = 0.f, sp = 0.f, stp = 0.f;
+  float bce = 0.f, sp = 0.f, stp = 0.f, st = 0.f, str = 0.f;
   int nt = 0, nr = 0, ntr = 0;
 };
 
@@ -39,21 +39,41 @@ __device__ __forceinline__ float sigmoid_and_softplus(float x, float& softplus_n
   return x >= 0.f ? inv : e * inv;
 }
 
+// The probabilities the caller gets back (forward()'s second output, roadmap_bce_v2.py:81): torch's own sequence
+// 1 / (1 + exp(-x)) with the accurate expf and an IEEE division, so that they agree with the reference's to the last
+// place or two -- and pinned to the binarisation rule, so that `probs.round()` (roadmap_bce_v2.py:72,140) IS the
+// binary map whatever expf's rounding of the few logits in (0, 2^-22): p > 0.5 exactly when x > 1.5 * 2^-24.
+__device__ __forceinline__ float sigmoid_exact(float x, bool r) {
+  float p = __fdiv_rn(1.0f, 1.0f + expf(-x));
+  if (r) p = fmaxf(p, __uint_as_float(0x3F000001u));   // smallest float above 0.5
+  else p = fminf(p, 0.5f);
+  return p;
+}
+
+template <bool EXACT_P>
 __device__ __forceinline__ void element(float x, float t, Acc& a, float& p, bool& r) {
   float sp;
   p = sigmoid_and_softplus(x, sp);
   // (1-t)*x + max(-x,0) + log1p(exp(-|x|))
   a.bce += (1.0f - t) * x + fmaxf(-x, 0.f) + sp;
   r = binarise(x);
+  if (EXACT_P) p = sigmoid_exact(x, r);
+  // helper.py:74-77 on float maps: tp = sum(a*b), denominator a.sum() + b.sum() - tp -- sums of the VALUES, so that a
+  // soft (non 0/1) target gets the reference's score too; the integer counts are kept beside them
+  const float rf = r ? 1.0f : 0.0f;
   a.sp += p;
   a.stp += t * p;
+  a.st += t;
+  a.str += t * rf;
   const int ti = t != 0.f;
   a.nt += ti;
   a.nr += r;
   a.ntr += ti & (int)r;
 }
 
-template <bool TU8>
+// TMODE: 0 = fp32 target, 1 = u8 / bool target, 2 = no target (read as all zero: forward()'s sigmoid + binary map).
+// EXACT_P: the probabilities are written out -> IEEE sigmoid (see sigmoid_exact); sums-only calls keep the MUFU path.
+template <int TMODE, bool EXACT_P>
 __global__ void __launch_bounds__(kThreads) bce_ts_kernel(const float* __restrict__ logits,
                                                           const void* __restrict__ target_,
                                                           float* __restrict__ probs,
@@ -67,36 +87,39 @@ __global__ void __launch_bounds__(kThreads) bce_ts_kernel(const float* __restric
   for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n4; i += stride) {
     const float4 x = __ldcs(reinterpret_cast<const float4*>(logits) + i);
     float4 t;
-    if (TU8) {
+    if (TMODE == 1) {
       const uchar4 u = __ldcs(reinterpret_cast<const uchar4*>(target_) + i);
       t = make_float4(u.x != 0, u.y != 0, u.z != 0, u.w != 0);
-    } else {
+    } else if (TMODE == 0) {
       t = __ldcs(reinterpret_cast<const float4*>(target_) + i);
+    } else {
+      t = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 p;
     bool r0, r1, r2, r3;
-    element(x.x, t.x, a, p.x, r0);
-    element(x.y, t.y, a, p.y, r1);
-    element(x.z, t.z, a, p.z, r2);
-    element(x.w, t.w, a, p.w, r3);
+    element<EXACT_P>(x.x, t.x, a, p.x, r0);
+    element<EXACT_P>(x.y, t.y, a, p.y, r1);
+    element<EXACT_P>(x.z, t.z, a, p.z, r2);
+    element<EXACT_P>(x.w, t.w, a, p.w, r3);
     if (probs) __stcs(reinterpret_cast<float4*>(probs) + i, p);
     if (binary) reinterpret_cast<uchar4*>(binary)[i] = make_uchar4(r0, r1, r2, r3);
   }
   // ragged tail (n % 4)
   for (long long i = (n4 << 2) + blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += stride) {
     const float x = logits[i];
-    const float t = TU8 ? (float)(reinterpret_cast<const uint8_t*>(target_)[i] != 0)
-                        : reinterpret_cast<const float*>(target_)[i];
+    const float t = TMODE == 1 ? (float)(reinterpret_cast<const uint8_t*>(target_)[i] != 0)
+                    : TMODE == 0 ? reinterpret_cast<const float*>(target_)[i] : 0.f;
     float p;
     bool r;
-    element(x, t, a, p, r);
+    element<EXACT_P>(x, t, a, p, r);
     if (probs) probs[i] = p;
     if (binary) binary[i] = r;
   }
 
   // CTA reduction in double / int64
   __shared__ double sred[kThreads / 32][kSlots];
-  double v[kSlots] = {(double)a.bce, (double)a.sp, (double)a.stp, (double)a.nt, (double)a.nr, (double)a.ntr};
+  double v[kSlots] = {(double)a.bce, (double)a.sp, (double)a.stp, (double)a.nt, (double)a.nr, (double)a.ntr,
+                      (double)a.st, (double)a.str};
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) v[s] = dd::warp_sum(v[s]);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -142,12 +165,13 @@ __global__ void __launch_bounds__(kThreads) bce_ts_kernel(const float* __restric
   if (threadIdx.x == 0) {
     const double bce = sred[0][0], sp = sred[0][1], stp = sred[0][2];
     const long long nt = (long long)sred[0][3], nr = (long long)sred[0][4], ntr = (long long)sred[0][5];
+    const double st = sred[0][6], str = sred[0][7];      // == nt, ntr for a 0/1 target
     stats[0] = (float)(bce / (double)n);
     // helper.py:74-77 in fp32: tp*1.0 / (a.sum() + b.sum() - tp)
     const float tpf = (float)stp;
-    stats[1] = tpf / (((float)nt + (float)sp) - tpf);
-    const float tpr = (float)ntr;
-    stats[2] = tpr / (((float)nt + (float)nr) - tpr);
+    stats[1] = tpf / (((float)st + (float)sp) - tpf);
+    const float tpr = (float)str;
+    stats[2] = tpr / (((float)st + (float)nr) - tpr);
     stats[3] = 0.f;
     counts[0] = nt; counts[1] = nr; counts[2] = ntr; counts[3] = n;
     ws->ticket = 0;  // self-reset for the next call on this stream
@@ -264,7 +288,7 @@ extern "C" size_t dd_bce_ts_workspace_bytes(void) { return sizeof(Workspace); }
 extern "C" int dd_bce_ts_fwd(const float* logits, const void* target, int target_is_u8, float* probs,
                              uint8_t* binary, float* stats, long long* counts, void* workspace,
                              size_t ws_bytes, long long n, void* stream) {
-  DD_REQUIRE(logits && target && stats && counts && workspace, DD_ERR_BAD_ARG, "dd_bce_ts_fwd: null pointer");
+  DD_REQUIRE(logits && stats && counts && workspace, DD_ERR_BAD_ARG, "dd_bce_ts_fwd: null pointer");
   DD_REQUIRE(n > 0, DD_ERR_BAD_ARG, "dd_bce_ts_fwd: n=%lld", n);
   DD_REQUIRE(ws_bytes >= sizeof(Workspace), DD_ERR_WORKSPACE, "dd_bce_ts_fwd: workspace %zu < %zu", ws_bytes,
              sizeof(Workspace));
@@ -272,12 +296,16 @@ extern "C" int dd_bce_ts_fwd(const float* logits, const void* target, int target
                  (!probs || (uintptr_t)probs % 16 == 0) && (!binary || (uintptr_t)binary % 4 == 0),
              DD_ERR_ALIGNMENT, "dd_bce_ts_fwd: pointers must be 16-byte aligned");
   const int grid = grid_for(n);
-  if (target_is_u8)
-    bce_ts_kernel<true><<<grid, kThreads, 0, dd::as_stream(stream)>>>(logits, target, probs, binary, stats, counts,
-                                                                      (Workspace*)workspace, n);
-  else
-    bce_ts_kernel<false><<<grid, kThreads, 0, dd::as_stream(stream)>>>(logits, target, probs, binary, stats, counts,
-                                                                       (Workspace*)workspace, n);
+  const int tmode = target == nullptr ? 2 : (target_is_u8 ? 1 : 0);
+  Workspace* ws = (Workspace*)workspace;
+  cudaStream_t st = dd::as_stream(stream);
+#define DD_BCE_LAUNCH(TM, EX) bce_ts_kernel<TM, EX><<<grid, kThreads, 0, st>>>(logits, target, probs, binary, stats, counts, ws, n)
+  if (probs) {
+    if (tmode == 0) DD_BCE_LAUNCH(0, true); else if (tmode == 1) DD_BCE_LAUNCH(1, true); else DD_BCE_LAUNCH(2, true);
+  } else {
+    if (tmode == 0) DD_BCE_LAUNCH(0, false); else if (tmode == 1) DD_BCE_LAUNCH(1, false); else DD_BCE_LAUNCH(2, false);
+  }
+#undef DD_BCE_LAUNCH
   return dd::check_launch("bce_ts_fwd");
 }
 

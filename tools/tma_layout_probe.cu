@@ -167,25 +167,25 @@ int main() {
   // ---------------------------------------------------------------- 2. element stride 2 along the pixel axis
   const int B = 1, H = 4, W = 256;          // the first 1024 pixels of hx seen as [1][4][256][32]
   CUtensorMap ms;
-  rc = encode_stride2(&ms, dx, B, H, W, 257);
-  printf("2. TMA box {8 ch, 257 px, element stride 2} -> expect 129 px x 16 B (encode rc %d)\n", rc);
+  rc = encode_stride2(&ms, dx, B, H, W, 255);        // box extents are capped at 256 SOURCE pixels: 255 -> 128 loaded
+  printf("2. TMA box {8 ch, 255 px, element stride 2} -> expect 128 px x 16 B (encode rc %d)\n", rc);
   if (rc == 0) {
     cudaFuncSetAttribute(probe_stride2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192);
     for (int w0 = -1; w0 <= 1; ++w0) {
       const int cg = 2, h = 1;
-      probe_stride2_kernel<<<1, 128, 8192>>>(ms, dplane, cg, w0, h, 0, 129 * 16);
+      probe_stride2_kernel<<<1, 128, 8192>>>(ms, dplane, cg, w0, h, 0, 128 * 16);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("   w0 %d: CUDA error %s (transaction bytes probably differ from 129 x 16)\n", w0, cudaGetErrorString(e)); return 1; }
       std::vector<__nv_bfloat16> hp(2048);
       cudaMemcpy(hp.data(), dplane, 4096, cudaMemcpyDeviceToHost);
       int bad = 0;
-      for (int i = 0; i < 129; ++i)
+      for (int i = 0; i < 128; ++i)
         for (int c = 0; c < 8; ++c) {
           const int w = w0 + 2 * i;
           const float ref = (w >= 0 && w < W) ? fx[((h * W) + w) * 32 + cg * 8 + c] : 0.f;
           if (__bfloat162float(hp[i * 8 + c]) != ref) ++bad;
         }
-      printf("   start w0 = %2d: %s (%d of %d elements differ)\n", w0, bad == 0 ? "PASS" : "FAIL", bad, 129 * 8);
+      printf("   start w0 = %2d: %s (%d of %d elements differ)\n", w0, bad == 0 ? "PASS" : "FAIL", bad, 128 * 8);
     }
   }
   return 0;
