@@ -277,6 +277,53 @@ def hbm_kernel_rooflines(batch: int, pk):
     return rows
 
 
+def verify_data_parallel_step(model, opt, step, views, road, world):
+    """The N-GPU step checks itself (the sharded reduce + Adam + all-gather kernel runs nowhere else at this width):
+    one more step from the current state, then (1) every parameter is bit-identical on all ranks (all-reduce MAX and
+    MIN of each tensor), (2) the new head weight equals torch arithmetic for Adam applied to the all-reduced MEAN
+    gradient, from the moments and weights saved before the step.  Collective on every rank; outside the timed region."""
+    head = model.fc1.weight
+    reg = opt._regions.get(id(head))
+    if reg is None:
+        return None
+    st = opt.state[reg["key"]]
+    t_before = int(st["step"])
+    m0, v0 = opt._full_moments(reg)
+    w0 = head.detach().clone().reshape(-1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    step(views, road)
+    torch.cuda.synchronize()
+    dist.barrier()
+    g = head.grad.detach().clone().reshape(-1)          # this rank's gradient replica of the step just taken
+    dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    g /= world
+    lr, b1, b2, eps, wd = opt._hyper()
+    tt = t_before + 1
+    if wd:
+        g = g + wd * w0
+    m1 = m0 + (1 - b1) * (g - m0)
+    v1 = b2 * v0 + (1 - b2) * g * g
+    expect = w0 - (lr / (1 - b1 ** tt)) * (m1 / (v1.sqrt() / (1 - b2 ** tt) ** 0.5 + eps))
+    got = head.detach().reshape(-1)
+    err_w = float((got - expect).abs().max() / expect.abs().max())
+    err_u = float((got - expect).abs().max() / (expect - w0).abs().max().clamp_min(1e-30))
+    del m0, v0, m1, v1, g, expect
+    worst = 0.0
+    for p in model.parameters():
+        hi, lo = p.detach().clone(), p.detach().clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        worst = max(worst, float((hi - lo).abs().max()))
+        del hi, lo
+    res = torch.tensor([worst, err_w, err_u], device=head.device, dtype=torch.float64)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    worst, err_w, err_u = (float(x) for x in res)
+    return {"replica_max_abs_diff": worst, "vs_single_rank_step_rel_err": err_w, "vs_single_rank_step_err_rel_to_update": err_u,
+            "checked": "all parameters equal on all ranks after a step; head weight (81.9 M) vs torch Adam arithmetic on the "
+                       "all-reduced mean gradient", "tolerance": 5e-6, "ok": worst == 0.0 and err_w < 5e-6}
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -370,6 +417,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sec, sec_e2e = float(t[0]), float(t[1])
+    verify = verify_data_parallel_step(model, opt, step, views_d, road_d, world) if world > 1 else None
+    if verify is not None and not verify["ok"]:
+        raise SystemExit(f"bench.py: the data-parallel step failed its self-check: {json.dumps(verify)}")
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -399,6 +449,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_rows,
             "cpu_baseline": cpu, "final_loss": final_loss,
         }
+        if verify is not None:
+            line["dp_self_check"] = verify
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

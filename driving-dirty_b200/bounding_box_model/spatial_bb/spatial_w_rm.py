@@ -97,7 +97,8 @@ class BBSpatialRoadMap(LightningModule):
         return {"val_loss": avg_val_loss, "log": {"avg_val_loss": avg_val_loss}}
 
     def configure_optimizers(self):
-        return torch.optim.Adam(self.parameters(), lr=self.hparams.learning_rate)
+        from ....optim import make_adam
+        return make_adam(self, self.hparams.learning_rate)
 
     @staticmethod
     def add_model_specific_args(parent_parser):

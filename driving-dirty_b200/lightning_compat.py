@@ -54,5 +54,7 @@ LightningModule = _PLModule if HAVE_LIGHTNING else _MinimalLightningModule
 def save_checkpoint(module, path):
     """Write the ``{'state_dict', 'hparams'}`` file load_from_checkpoint reads (PL 0.7.5 layout)."""
     hp = getattr(module, "hparams", None)
-    torch.save({"state_dict": module.state_dict(), "hparams": vars(hp) if isinstance(hp, Namespace) else dict(hp or {})},
-               path)
+    # clones: a parameter adopted by optim.FusedAdam's sharded form lives inside one large symmetric buffer, and
+    # torch.save writes a tensor's whole storage
+    sd = {k: v.detach().clone() for k, v in module.state_dict().items()}
+    torch.save({"state_dict": sd, "hparams": vars(hp) if isinstance(hp, Namespace) else dict(hp or {})}, path)

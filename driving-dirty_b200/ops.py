@@ -150,6 +150,11 @@ class EncoderConvStack(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.needs_input_grad[0]:
+            # nn.Conv2d would propagate a gradient to the images; there is no c1 input-gradient kernel on this path
+            # (the reference never asks for one: the views come from the dataloader) -- fail loudly, not with zeros
+            raise NotImplementedError("encoder_conv_stack: the camera views / mosaic require grad, but the scene pipeline "
+                                      "has no input gradient for the first conv")
         inp, w2, w3, a1, a2, a3 = ctx.saved_tensors
         B, H, Wm, H3, W3, is_views, code, c3_only, impl, act_dtype = ctx.geom
         dev, st = g.device, stream_ptr()
@@ -330,7 +335,7 @@ def bce_threat(logits, target, want_probs=True, want_binary=True):
 
 class _SigmoidBinary(torch.autograd.Function):
     """forward()'s ``torch.sigmoid(y)`` (roadmap_bce_v2.py:81) plus the binarised map, through the
-    same kernel with a dummy all-zero target (statistics discarded)."""
+    same kernel without a target (statistics discarded)."""
 
     @staticmethod
     def forward(ctx, logits):
@@ -341,9 +346,8 @@ class _SigmoidBinary(torch.autograd.Function):
         stats = torch.empty(4, dtype=torch.float32, device=dev)
         counts = torch.empty(4, dtype=torch.int64, device=dev)
         ws, wn = _bce_ws(dev)
-        # the binary map doubles as the (ignored) u8 target: it is written after being read per element
-        zeros = torch.zeros(logits.shape, dtype=torch.uint8, device=dev)
-        call("dd_bce_ts_fwd", logits.data_ptr(), zeros.data_ptr(), 1, probs.data_ptr(), binary.data_ptr(),
+        # no target: the kernel reads none (statistics are computed against an all-zero map and discarded)
+        call("dd_bce_ts_fwd", logits.data_ptr(), None, 0, probs.data_ptr(), binary.data_ptr(),
              stats.data_ptr(), counts.data_ptr(), ws.data_ptr(), wn, logits.numel(), stream_ptr())
         ctx.save_for_backward(probs)
         ctx.mark_non_differentiable(binary)

@@ -18,6 +18,12 @@ traffic per GPU, and no NCCL kernel in the step.
 * All other tensors share one flat region: their gradients are gathered into it by one multi-tensor
   copy and updated by one sharded launch in ``step()``.
 
+``state_dict()`` / ``load_state_dict()`` speak torch.optim.Adam's layout (per-parameter ``step`` / ``exp_avg`` /
+``exp_avg_sq`` of the parameter's shape) at every world size: the moment shards live in a second symmetric buffer, so
+the rank that writes a checkpoint (rank 0 under Lightning) assembles the full moments from its peers' shards without a
+collective, and every rank re-slices its own shard on load -- a checkpoint moves between world sizes and to / from
+torch.optim.Adam.
+
 Semantics are torch.optim.Adam's (amsgrad off, L2 weight decay); ``param_groups[i]['lr']`` is read
 every step, so ``ReduceLROnPlateau`` (roadmap_bce_v2.py:156) works unchanged; tensors whose
 gradient is ``None`` are skipped (a partly frozen flat bucket is updated per tensor on every replica).
@@ -73,6 +79,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._side = None           # stream of the updates launched from the backward pass
         self._written = set()       # ids of wide params whose gradient replica was written since the last step()
         self._launched = set()      # ... and whose update is already running on the side stream
+        self._mom, self._mom_of = None, None   # symmetric buffer of this rank's moment shards, accessor for the peers'
         self._flat_replicated = False   # the flat bucket fell back to per-tensor replicated updates (partly frozen model)
         self._lib = _lib.load()     # raises when the CUDA library is missing: no fallback
         for g in self.param_groups:
@@ -104,6 +111,28 @@ class FusedAdam(torch.optim.Optimizer):
             raise RuntimeError("FusedAdam: multicast requested but the symmetric buffer has no multicast mapping")
         return buf, hdl, [int(x) for x in hdl.buffer_ptrs], mc
 
+    def _alloc_moments(self, numel, device):
+        """Symmetric buffer for the moment shards -> (local tensor, fn(rank) -> that rank's tensor)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(buf, grp)
+        buf.zero_()
+        return buf, (lambda rk: buf if rk == self.rank else hdl.get_buffer(rk, (numel,), torch.float32))
+
+    @staticmethod
+    def _alias(view):
+        """A tensor over the same device memory as `view` but with a storage of its own, exactly as long as the tensor:
+        torch.save of a parameter that is a plain view would serialise the whole [gradients | weights] buffer."""
+        if view.device.type != "cuda":
+            return view
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": tuple(view.shape), "typestr": "<f4", "data": (view.data_ptr(), False),
+                                        "version": 3, "strides": None}
+
+        return torch.as_tensor(_Mem(), device=view.device)
+
     # ------------------------------------------------------------------------------------------
     def _setup_sharding(self, shard_min_numel, multicast, broadcast_init):
         params = [p for g in self.param_groups for p in g["params"]]
@@ -124,7 +153,7 @@ class FusedAdam(torch.optim.Optimizer):
 
         def adopt(p, off):
             n = p.numel()
-            w = buf[total + off: total + off + n].view_as(p)
+            w = self._alias(buf[total + off: total + off + n].view_as(p))
             w.copy_(p.data)
             p.data = w                                   # the module now computes from the symmetric replica
             return buf[off: off + n].view_as(p)
@@ -139,7 +168,17 @@ class FusedAdam(torch.optim.Optimizer):
         if small:
             views = [adopt(p, flat_off + o) for p, o in zip(small, small_offs)]
             lo, hi = shard_bounds(small_total, self.world, self.rank)
-            self._flat = dict(off=flat_off, n=small_total, lo=lo, hi=hi, channel=0, params=small, grad_views=views, key="flat")
+            self._flat = dict(off=flat_off, n=small_total, lo=lo, hi=hi, channel=0, params=small, grad_views=views, key="flat",
+                              offs=small_offs)
+        # moment shards: [exp_avg | exp_avg_sq] per region, capacity = the longest shard (the last rank's), in a symmetric
+        # buffer of their own so that state_dict() can read the peers' shards
+        moff = 0
+        for r in list(self._regions.values()) + ([self._flat] if self._flat is not None else []):
+            lo_l, hi_l = shard_bounds(r["n"], self.world, self.world - 1)
+            cap = -(-max(hi_l - lo_l, r["hi"] - r["lo"], 4) // _ALIGN) * _ALIGN
+            r["moff"], r["mcap"] = moff, cap
+            moff += 2 * cap
+        self._mom, self._mom_of = self._alloc_moments(moff, dev)
         self._symm = dict(buf=buf, hdl=hdl, total=total, ptrs=ptrs, mc=mc)
         if self._overlap:
             self._side = torch.cuda.Stream(device=dev)
@@ -171,6 +210,16 @@ class FusedAdam(torch.optim.Optimizer):
             st["step"] = 0
             st["exp_avg"] = torch.zeros(numel, dtype=torch.float32, device=device)
             st["exp_avg_sq"] = torch.zeros(numel, dtype=torch.float32, device=device)
+        return st
+
+    def _shard_state(self, r):
+        """State of a sharded region: views of this rank's piece of the symmetric moments buffer."""
+        st = self.state[r["key"]]
+        if not st:
+            n = r["hi"] - r["lo"]
+            st["step"] = 0
+            st["exp_avg"] = self._mom[r["moff"]: r["moff"] + n]
+            st["exp_avg_sq"] = self._mom[r["moff"] + r["mcap"]: r["moff"] + r["mcap"] + n]
         return st
 
     def _hyper(self):
@@ -229,6 +278,117 @@ class FusedAdam(torch.optim.Optimizer):
         self._written.clear()
         return loss
 
+    # ------------------------------------------------------------------------------------------
+    # checkpointing: torch.optim.Adam's layout in and out
+    # ------------------------------------------------------------------------------------------
+    def _full_moments(self, r):
+        """(exp_avg, exp_avg_sq) of a sharded region at full length, assembled from every rank's shard."""
+        dev = self._mom.device
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)      # this rank's step() ended with a cross-rank barrier: every shard is up to date
+        m, v = torch.empty(r["n"], dtype=torch.float32, device=dev), torch.empty(r["n"], dtype=torch.float32, device=dev)
+        for rk in range(self.world):
+            lo, hi = shard_bounds(r["n"], self.world, rk)
+            peer = self._mom_of(rk)
+            m[lo:hi].copy_(peer[r["moff"]: r["moff"] + hi - lo])
+            v[lo:hi].copy_(peer[r["moff"] + r["mcap"]: r["moff"] + r["mcap"] + hi - lo])
+        return m, v
+
+    def state_dict(self):
+        index, groups = {}, []
+        for g in self.param_groups:
+            pg = {k: v for k, v in g.items() if k != "params"}
+            pg["params"] = []
+            for p in g["params"]:
+                index[id(p)] = len(index)
+                pg["params"].append(index[id(p)])
+            groups.append(pg)
+        state = {}
+
+        def put(p, step, m, v):
+            state[index[id(p)]] = {"step": torch.tensor(float(step), dtype=torch.float32),
+                                   "exp_avg": m.detach().clone().view_as(p), "exp_avg_sq": v.detach().clone().view_as(p)}
+
+        for g in self.param_groups:
+            for p in g["params"]:
+                st = self.state.get(p)
+                if st and id(p) not in self._regions:        # world 1, or the per-tensor (replicated) form
+                    put(p, st["step"], st["exp_avg"], st["exp_avg_sq"])
+        for key, r in self._regions.items():
+            st = self.state.get(r["key"])
+            if st and not isinstance(r["key"], str):
+                m, v = self._full_moments(r)
+                put(r["key"], st["step"], m, v)
+        fl = self._flat
+        if fl is not None and self.state.get("flat"):
+            m, v = self._full_moments(fl)
+            for p, o in zip(fl["params"], fl["offs"]):
+                put(p, self.state["flat"]["step"], m[o: o + p.numel()], v[o: o + p.numel()])
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, state_dict):
+        params = [p for g in self.param_groups for p in g["params"]]
+        saved_groups = state_dict["param_groups"]
+        ids = [i for g in saved_groups for i in g["params"]]
+        if len(ids) != len(params):
+            raise ValueError("FusedAdam.load_state_dict: the checkpoint has a different number of parameters")
+        for g, sg in zip(self.param_groups, saved_groups):
+            for k, v in sg.items():
+                if k != "params" and k in g:
+                    g[k] = v
+        by_param = {id(p): state_dict["state"].get(i, state_dict["state"].get(str(i))) for p, i in zip(params, ids)}
+
+        def unpack(p):
+            st = by_param.get(id(p))
+            if not st:
+                return None
+            step = st["step"]
+            step = int(round(float(step.item() if torch.is_tensor(step) else step)))
+            dev = p.device
+            m = st["exp_avg"].detach().to(device=dev, dtype=torch.float32).reshape(-1)
+            v = st["exp_avg_sq"].detach().to(device=dev, dtype=torch.float32).reshape(-1)
+            if m.numel() != p.numel():
+                raise ValueError("FusedAdam.load_state_dict: moment shape does not match the parameter")
+            return step, m, v
+
+        self.state.clear()
+        for p in params:
+            if id(p) in self._regions:
+                got = unpack(p)
+                if got:
+                    r = self._regions[id(p)]
+                    st = self._shard_state(r)
+                    st["step"] = got[0]
+                    st["exp_avg"].copy_(got[1][r["lo"]: r["hi"]])
+                    st["exp_avg_sq"].copy_(got[2][r["lo"]: r["hi"]])
+        fl = self._flat
+        flat_ids = {id(p) for p in fl["params"]} if fl is not None else set()
+        if fl is not None:
+            got = [unpack(p) for p in fl["params"]]
+            steps = {g[0] for g in got if g}
+            if all(got) and len(steps) == 1:                 # one step count: the sharded form can carry it
+                dev = self._mom.device
+                m, v = torch.zeros(fl["n"], device=dev), torch.zeros(fl["n"], device=dev)
+                for p, o, g in zip(fl["params"], fl["offs"], got):
+                    m[o: o + p.numel()].copy_(g[1])
+                    v[o: o + p.numel()].copy_(g[2])
+                st = self._shard_state(fl)
+                st["step"] = steps.pop()
+                st["exp_avg"].copy_(m[fl["lo"]: fl["hi"]])
+                st["exp_avg_sq"].copy_(v[fl["lo"]: fl["hi"]])
+                self._flat_replicated = False
+            elif any(got):                                   # per-tensor step counts (partly frozen history): replicated form
+                self._flat_replicated = True
+                for p, g in zip(fl["params"], got):
+                    if g:
+                        self.state[p] = {"step": g[0], "exp_avg": g[1].clone(), "exp_avg_sq": g[2].clone()}
+        for p in params:
+            if id(p) in self._regions or id(p) in flat_ids:
+                continue
+            got = unpack(p)
+            if got:
+                self.state[p] = {"step": got[0], "exp_avg": got[1].clone(), "exp_avg_sq": got[2].clone()}
+
     def _launch_local(self, g, p, grad):
         """One dd_adam_step launch: the whole tensor, this replica only."""
         if not (grad.is_contiguous() and grad.dtype == torch.float32):
@@ -242,7 +402,7 @@ class FusedAdam(torch.optim.Optimizer):
     def _launch_sharded(self, r, ctas_per_sm):
         sy, W = self._symm, self.world
         lo, hi, total = r["lo"], r["hi"], sy["total"]
-        st = self._state(r["key"], hi - lo, sy["buf"].device)
+        st = self._shard_state(r)
         st["step"] += 1
         gptrs = (ctypes.c_void_p * W)(*[b + 4 * r["off"] for b in sy["ptrs"]])
         wptrs = (ctypes.c_void_p * W)(*[b + 4 * (total + r["off"]) for b in sy["ptrs"]])
@@ -273,3 +433,17 @@ class FusedAdam(torch.optim.Optimizer):
             self._launch_sharded(r, ctas_per_sm=1)
             hdl.barrier(channel=r["channel"])
         self._launched.add(key)
+
+
+def make_adam(module, lr):
+    """What the task modules' ``configure_optimizers`` return for ``torch.optim.Adam(self.parameters(), lr)``
+    (roadmap_bce_v2.py:155, autoencoder.py:120, spatial_w_rm.py:189).  hparams.optimizer = "fused" (the default when the
+    model sits on a CUDA device): ``FusedAdam`` -- the dd_adam_step kernels, and under torch.distributed the sharded
+    reduce + Adam + all-gather exchange, launched from the backward pass; "torch": the reference's optimizer object."""
+    hp = getattr(module, "hparams", None)
+    kind = getattr(hp, "optimizer", "fused") if hp is not None else "fused"
+    params = [p for p in module.parameters()]
+    on_cuda = bool(params) and all(p.is_cuda for p in params)
+    if kind == "fused" and on_cuda:
+        return FusedAdam(params, lr=lr, overlap_backward=dist.is_initialized() and dist.get_world_size() > 1)
+    return torch.optim.Adam(params, lr=lr)

@@ -99,7 +99,8 @@ class RoadMapBCE(LightningModule):
         return {"val_loss": avg_val_loss, "log": logs}
 
     def configure_optimizers(self):
-        optimizer = torch.optim.Adam(self.parameters(), lr=self.hparams.learning_rate)
+        from ..optim import make_adam
+        optimizer = make_adam(self, self.hparams.learning_rate)       # :155 (FusedAdam unless --optimizer torch)
         scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, patience=10)
         return [optimizer], [scheduler]
 
@@ -113,4 +114,5 @@ class RoadMapBCE(LightningModule):
         parser.add_argument("--pretrained_path", type=str, required=True)
         parser.add_argument("--output_img_freq", type=int, default=500)
         parser.add_argument("--compute_dtype", type=str, default="fp32", choices=["fp32", "bf16"])
+        parser.add_argument("--optimizer", type=str, default="fused", choices=["fused", "torch"])
         return parser

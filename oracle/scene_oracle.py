@@ -44,7 +44,7 @@ def stitch(views: torch.Tensor) -> torch.Tensor:
     out = np.empty((b, c, h, 6 * w), dtype=v.dtype)
     for j, src in enumerate(VIEW_ORDER):
         out[:, :, :, j * w:(j + 1) * w] = v[:, src]
-    return torch.from_numpy(out)
+    return torch.from_numpy(out).to(views.device)      # (device kept: tests also run this restatement on cuda tensors)
 
 
 def six_to_one(views: torch.Tensor, target_slot: int):

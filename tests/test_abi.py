@@ -108,7 +108,6 @@ def test_c_oracle_matches_numpy_oracle():
     t = (torch.rand(1000) > 0.5)
     cnt = (ctypes.c_longlong * 3)()
     lib.oracle_ts_counts(fp(t.numpy().astype(np.uint8)), fp(bo), ctypes.c_longlong(1000), cnt)
-    assert tuple(cnt) == so.threat_score_counts(t.float(), torch.from_numpy(bo).float())[1::-1] + (cnt[2],) or True
     tp, nt, nr = so.threat_score_counts(t.float(), torch.from_numpy(bo).float())
     assert (cnt[0], cnt[1], cnt[2]) == (nt, nr, tp)
     lib.oracle_bce_mean.restype = ctypes.c_double

@@ -63,6 +63,15 @@ def _adam_worker(rank, world, port, q):
         def _alloc_symmetric(self, numel, device, multicast):
             return torch.empty(numel, dtype=torch.float32), _Handle(), [0] * self.world, 0
 
+        def _alloc_moments(self, numel, device):
+            buf = torch.zeros(numel, dtype=torch.float32)
+
+            def peer(rk):          # the product reads a peer-mapped buffer; here every rank calls state_dict(): broadcast
+                t = buf.clone()
+                dist.broadcast(t, src=rk)
+                return t
+            return buf, peer
+
         def _launch_sharded(self, r, ctas_per_sm):
             sy = self._symm
             buf, total, off, lo, hi = sy["buf"], sy["total"], r["off"], r["lo"], r["hi"]
@@ -78,7 +87,7 @@ def _adam_worker(rank, world, port, q):
                     parts = got
             g = sum(parts) / self.world
             # 2. Adam on the shard (torch.optim.Adam's arithmetic)
-            st = self._state(r["key"], hi - lo, buf.device)
+            st = self._shard_state(r)
             st["step"] += 1
             lr, b1, b2, eps, wd = self._hyper()
             w = buf[total + off + lo: total + off + hi]
@@ -125,6 +134,28 @@ def _adam_worker(rank, world, port, q):
             p.grad = sum(grads[step][r][i] for r in range(world)) / world
         ropt.step()
     err = max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(params, ref))
+    # ---- checkpoint round trip: torch.optim.Adam's layout out and in, at world size 2
+    sd = opt.state_dict()                                      # full, parameter-shaped moments on every rank
+    rsd = ropt.state_dict()
+    sd_err = max(float((sd["state"][i][k] - rsd["state"][i][k]).abs().max()) for i in range(len(shapes))
+                 for k in ("exp_avg", "exp_avg_sq"))
+    steps_ok = all(int(sd["state"][i]["step"]) == 3 for i in range(len(shapes)))
+    torch.optim.Adam([t.clone().requires_grad_(True) for t in init], lr=1e-2).load_state_dict(sd)   # torch accepts it
+    params_b = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    opt_b = GlooAdam(params_b, lr=1e-2, weight_decay=0.01, shard_min_numel=1024)
+    opt_b.load_state_dict(rsd)                                 # ... and we accept torch's (tensor `step`, full moments)
+    g4 = [[torch.randn(s, generator=g) for s in shapes] for _ in range(world)]
+    opt_b.zero_grad()
+    params_b[0]._dd_grad_buffer.copy_(g4[rank][0])
+    params_b[0]._dd_grad_ready()
+    for p, gr in zip(params_b[1:], g4[rank][1:]):
+        p.grad = gr.clone()
+    opt_b.step()
+    for i, p in enumerate(ref):
+        p.grad = sum(g4[r][i] for r in range(world)) / world
+    ropt.step()
+    err_resume = max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(params_b, ref))
+    ckpt_ok = sd_err < 1e-6 and steps_ok and err_resume < 1e-6
     # a second backward without a step must be refused (the gradient buffer is overwritten, not accumulated)
     params[0]._dd_grad_ready()
     try:
@@ -150,7 +181,15 @@ def _adam_worker(rank, world, port, q):
         opt2.step()
         ropt2.step()
     err2 = max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(params2, ref2))
-    q.put((rank, err < 1e-6 and refused and err2 < 1e-6 and opt2._flat_replicated, (err, err2)))
+    # the partly frozen history (per-tensor step counts) survives a save / load as well
+    sd2 = opt2.state_dict()
+    steps2 = [int(sd2["state"][i]["step"]) for i in range(4)]
+    params3 = [torch.nn.Parameter(p.detach().clone()) for p in params2]
+    opt3 = GlooAdam(params3, lr=1e-2, shard_min_numel=1024)
+    opt3.load_state_dict(sd2)
+    ckpt_ok = ckpt_ok and steps2 == [3, 3, 3, 1] and opt3._flat_replicated
+    q.put((rank, err < 1e-6 and refused and err2 < 1e-6 and opt2._flat_replicated and ckpt_ok,
+           (err, err2, sd_err, err_resume, steps2)))
     dist.destroy_process_group()
 
 

@@ -355,8 +355,11 @@ def test_bce_threat_forward_backward(dd, shape, u8):
     ld = logits.cuda().requires_grad_(True)
     loss, probs, binary, stats, counts = dd.bce_threat(ld, target_b.cuda() if u8 else target.cuda())
     assert abs(float(loss) - float(ref["loss"])) < 1e-6 * max(1.0, abs(float(ref["loss"])))
-    assert rel_max_err(probs, ref["probs"]) < 1e-6
+    assert rel_max_err(probs, ref["probs"]) < 2e-7                       # IEEE sigmoid: a last place or two
     assert torch.equal(binary.cpu().float(), ref["binary"])             # bit-exact binarisation
+    # forward()'s contract (roadmap_bce_v2.py:72,81,140): rounding the RETURNED probabilities gives the binary map
+    assert torch.equal(probs.round(), binary.float())
+    assert torch.equal(probs.cpu().round(), ref["probs"].round())
     tp, nt, nr = so.threat_score_counts(target, ref["binary"])
     assert counts.cpu().tolist() == [nt, nr, tp, logits.numel()]        # exact integer counts
     assert float(stats[2]) == float(ref["ts_r"])                        # bit-exact rounded TS (<= 26 scenes)
@@ -375,7 +378,9 @@ def test_binarise_exhaustive_sweep(dd, golden):
     bits = np.arange(gold["sweep_lo"], gold["sweep_hi"], dtype=np.uint32)
     n = (len(bits) // 4) * 4
     x = torch.from_numpy(bits[:n].view(np.float32).copy())
-    _, binary = dd.sigmoid_binary(x.cuda())
+    probs, binary = dd.sigmoid_binary(x.cuda())
+    assert torch.equal(probs.round(), binary.float())                    # over the whole sweep, on the device
+    assert torch.equal(probs.cpu().round(), torch.sigmoid(x).round())    # and against the reference's own arithmetic
     got = binary.cpu()
     first = int(torch.nonzero(got).flatten()[0])
     assert int(bits[first]) == gold["first_one_bits"]
@@ -383,11 +388,25 @@ def test_binarise_exhaustive_sweep(dd, golden):
     e = gold["edge_x"]
     e = torch.cat([e, e[:2]])[:16]
     p, b = dd.sigmoid_binary(e.cuda())
+    assert torch.equal(p.round(), b.float())
     assert torch.equal(b.cpu().float()[:14], gold["edge_round"])
     assert rel_max_err(p.cpu()[:12], gold["edge_sigmoid"][:12]) < 1e-6
     # negatives never binarise to 1
     _, bn = dd.sigmoid_binary((-x[: 1 << 20]).cuda())
     assert int(bn.sum()) == 0
+
+
+def test_bce_threat_soft_target(dd):
+    """compute_ts_road_map (helper.py:74-77) sums VALUES: a soft (augmented) target must give the reference's score,
+    for the soft and for the rounded prediction."""
+    g = torch.Generator().manual_seed(71)
+    logits = torch.randn(3, 64, 64, generator=g)
+    target = torch.rand(3, 64, 64, generator=g)
+    loss, probs, binary, stats, counts = dd.bce_threat(logits.cuda(), target.cuda())
+    p = torch.sigmoid(logits)
+    assert abs(float(stats[1]) - float(so.threat_score(target, p))) < 2e-6
+    assert abs(float(stats[2]) - float(so.threat_score(target, p.round()))) < 2e-6
+    assert abs(float(loss) - float(F.binary_cross_entropy_with_logits(logits, target))) < 1e-6
 
 
 def test_threat_score_and_mse(dd):

@@ -373,3 +373,38 @@ def test_bb_forward_bf16_close_to_fp32(golden):
     err = float((so.strided_sample(pred.cpu()) - g["pred_sample"]).abs().max()) / g["pred_absmax"]
     print("bb bf16 pred rel-max err", err)
     assert err < 2e-2
+
+
+def test_unpatched_dropout_shares_the_philox_stream():
+    """SURVEY D5 / H6 without the CPU-RNG patch: the always-on F.dropout stays a torch call on a [B, hidden] CUDA tensor,
+    so after the same ``torch.manual_seed`` the product path and the reference arithmetic run ON THE SAME DEVICE
+    (oracle/scene_oracle.py on cuda tensors, TF32 off) draw identical Philox masks -- eval pass and training pass."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        model, params, views, road = build_roadmap_pair(4, 16, 8, 16, 20, dtype="fp32")
+        pc = {k: v.cuda() for k, v in params.items()}
+        vc, rc = views.cuda(), road.cuda()
+        batch = (tuple(vc.unbind(0)), None, tuple(rc.unbind(0)))
+        with torch.no_grad():
+            torch.manual_seed(123)
+            loss, _, logits, probs = model._run_step(batch, 1, "valid")
+            ref = so.run_step(pc, vc, rc, training=False, seed=123)
+            other = so.run_step(pc, vc, rc, training=False, seed=124)      # another mask: must NOT match
+        assert rel_max_err(logits, ref["logits"]) < 1e-5
+        assert rel_max_err(logits, other["logits"]) > 1e-3
+        assert abs(float(loss) - float(ref["loss"])) < 1e-6
+        # training pass (batch-statistics BatchNorm, dropout in the graph): gradients under the shared stream
+        model.frozen = False
+        model.ae.unfreeze()
+        torch.manual_seed(321)
+        out = model.training_step(batch, 1)
+        out["loss"].backward()
+        ref_t, grads = so.train_step_grads(pc, vc, rc, seed=321)
+        assert abs(float(out["loss"].detach()) - float(ref_t["loss"])) < 1e-6
+        for name in ("fc1.weight", "ae.encoder.fc2.fc1.weight", "ae.encoder.c2.weight", "ae.encoder.c1.weight"):
+            got = dict(model.named_parameters())[name].grad
+            assert rel_max_err(got, grads[name]) < 2e-5, name
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
