@@ -817,40 +817,10 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
 }
 
 // ================================================================================================
-// Weight gradient on the tensor cores (stride 1):
-//   dW[co][ci][kh][kw] = sum_{b,h,w} x[b,h+kh-1,w+kw-1,ci] * dy[b,h,w,co]
-// The contraction runs over PIXELS, so both operands are MN-major: A = x planes (M = 4 input rows x
-// 32 ci = 128), B = dy planes (N = 2 dy rows x 32 co = 64), K = 16 pixels per tcgen05.mma.  For the
-// dy-row pair (h, h+1) and x rows h-1..h+2, block (r, q) of D holds tap kh = r - q; 6 of the 8
-// blocks are useful.  kw is again a 16-byte shift of the A start address, one 64-column TMEM
-// accumulator per kw, accumulated over every work item of the CTA and written out ONCE at the end
-// as [cta][q][tap][ci][co] partials that an ordered reduction kernel folds (deterministic).
-// Stage = 4 dy rows + 6 x rows of a 128-pixel column strip, double buffered; warps 0..3 are
-// cp.async producers and run the final epilogue, warp 4 issues the MMAs.
+// The weight gradients of c2 / c3 live in conv_wgrad_tc.cu (rolling row ring, whole-pixel TMA boxes).
+// Shared pieces of the c1 weight-gradient kernel below:
 // ================================================================================================
-// Stride 2 (c3): one dy row per stage, x rows 2ho-1..2ho+1 (+ one junk row that only feeds the unused
-// D block r = 3) in [parity][row][cg] planes so that the (row, cg) chunks keep one uniform stride;
-// N = 32, every useful block has q = 0.
 constexpr int PSD = TILE_M * 16;                 // dy plane stride (128 pixels)
-template <int STRIDE>
-struct WgGeo {
-  static constexpr int ROWS = STRIDE == 1 ? 4 : 1;            // dy rows per stage
-  static constexpr int XROWS = STRIDE == 1 ? 6 : 3;           // x rows loaded per stage
-  // stride 2: the A operand spans 4 rows but only 3 are stored; the 4th (junk, feeds only the unused D block) reads
-  // whatever follows in the stage -- the next parity's rows or the dy planes
-  static constexpr int XROWS_ALLOC = STRIDE == 1 ? 6 : 3;
-  // Stages in flight (stride 1: 2 x 85 KB; stride 2: 3 x 59 KB).  Smaller stride-1 stages (2 dy + 4 x rows, 4 deep) were
-  // measured slower (0.87 vs 0.77 ms): the cp.async producers, not the stage count, bound this kernel.
-  static constexpr int NST = STRIDE == 1 ? 2 : 3;
-  static constexpr int XPIX = STRIDE == 1 ? 130 : 257;        // x pixels per row
-  static constexpr int X_BYTES = STRIDE * XROWS_ALLOC * 4 * PS;
-  static constexpr int DY_BYTES = ROWS * 4 * PSD;
-  static constexpr int STAGE_BYTES = X_BYTES + DY_BYTES;
-  static constexpr int SMEM = NST * STAGE_BYTES + 1024;
-  static constexpr int NQ = STRIDE == 1 ? 2 : 1;              // q slots in the per-CTA partials
-  static constexpr int PARTIAL = NQ * 9 * C * C;              // floats per CTA
-  static constexpr int N = 32 * NQ;
-};
 
 struct WgBars {
   uint64_t full[4], empty[4], done;
@@ -858,235 +828,6 @@ struct WgBars {
 };
 
 constexpr int WG_THREADS = 160;
-template <int STRIDE>
-__global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_c32_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x,
-                                                                       const __grid_constant__ CUtensorMap map_dy,
-                                                                       const __nv_bfloat16* __restrict__ x,
-                                                                       const __nv_bfloat16* __restrict__ dy,
-                                                                       float* __restrict__ partial, float* __restrict__ db_partial, int B, int H,
-                                                                       int W, int Ho, int Wo) {
-  using G = WgGeo<STRIDE>;
-  constexpr int WG_ROWS = G::ROWS, WG_XROWS = G::XROWS, WG_X_BYTES = G::X_BYTES, WG_STAGE_BYTES = G::STAGE_BYTES;
-  constexpr int WG_PARTIAL = G::PARTIAL;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  WgBars* bars = reinterpret_cast<WgBars*>(smem + G::NST * WG_STAGE_BYTES);
-  __shared__ float s_db[2][C];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: role code stays on the uniform datapath
-  const int wtiles = (Wo + TILE_M - 1) / TILE_M;
-  const int hsegs = (Ho + WG_ROWS - 1) / WG_ROWS;
-  const int items = B * wtiles * hsegs;
-
-  if (tid == 0) {
-    for (int i = 0; i < G::NST; ++i) { umma::mbar_init(&bars->full[i], STRIDE == 1 ? 1 : 128); umma::mbar_init(&bars->empty[i], STRIDE == 1 ? 3 : 1); }
-    umma::mbar_init(&bars->done, 1);
-    umma::fence_mbar_init();
-  }
-  if (warp == 4) umma::tmem_alloc(&bars->tmem_base, 256);
-  umma::tc_fence_before_sync();
-  __syncthreads();
-  umma::tc_fence_after_sync();
-  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
-
-  if (warp < 4 && STRIDE == 1) {
-    // =========================== producer (stride 1): one thread, TMA ============================
-    // one [pixels][8 ch] box per (row, channel group) plane, rows / columns outside the image zero-filled (see the
-    // stride-1 forward kernel); 24 x boxes + 16 dy boxes per stage on one transaction barrier
-    if (tid == 0) {
-      umma::tma_prefetch_desc(&map_x);
-      umma::tma_prefetch_desc(&map_dy);
-      uint32_t n = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
-        const int h0 = hs * WG_ROWS, w0 = wt * TILE_M;
-        const uint32_t stage = n % G::NST;
-        umma::mbar_wait(&bars->empty[stage], ((n / G::NST) & 1) ^ 1);
-        const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
-        const uint32_t ds = xs + WG_X_BYTES;
-        umma::mbar_expect_tx(&bars->full[stage], (uint32_t)(WG_XROWS * 4 * G::XPIX * 16 + WG_ROWS * 4 * TILE_M * 16));
-#pragma unroll 1
-        for (int r = 0; r < WG_XROWS; ++r)
-#pragma unroll
-          for (int cg = 0; cg < 4; ++cg)
-            umma::tma_load_4d(xs + (r * 4 + cg) * PS, &map_x, cg * 8, w0 - 1, h0 - 1 + r, b, &bars->full[stage]);
-#pragma unroll 1
-        for (int r = 0; r < WG_ROWS; ++r)
-#pragma unroll
-          for (int cg = 0; cg < 4; ++cg)
-            umma::tma_load_4d(ds + (r * 4 + cg) * PSD, &map_dy, cg * 8, w0, h0 + r, b, &bars->full[stage]);
-      }
-    } else if (warp == 1 || warp == 2) {
-      // =========================== bias gradient (stride 1): db[co] = sum of dy over pixels ========
-      // The dy planes are in shared memory anyway: two otherwise idle warps add them up per stage (thread = pixel
-      // column, 32 fp32 accumulators = one per channel), instead of a separate kernel reading dy from HBM again.
-      float acc[C];
-#pragma unroll
-      for (int k = 0; k < C; ++k) acc[k] = 0.f;
-      const int px0 = (warp - 1) * 32 + lane;              // pixels px0 and px0 + 64 of the strip
-      uint32_t n = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const uint32_t stage = n % G::NST;
-        umma::mbar_wait(&bars->full[stage], (n / G::NST) & 1);
-        const uint32_t ds = umma::smem_u32(smem + stage * WG_STAGE_BYTES) + WG_X_BYTES;
-#pragma unroll
-        for (int pl = 0; pl < WG_ROWS * 4; ++pl) {           // plane = (dy row, channel group)
-#pragma unroll
-          for (int hpx = 0; hpx < 2; ++hpx) {
-            uint32_t q0, q1, q2, q3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3)
-                         : "r"(ds + pl * PSD + (px0 + 64 * hpx) * 16));
-            const uint32_t qq[4] = {q0, q1, q2, q3};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[k]));
-              acc[(pl & 3) * 8 + 2 * k] += f.x;
-              acc[(pl & 3) * 8 + 2 * k + 1] += f.y;
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive(&bars->empty[stage]);
-      }
-#pragma unroll
-      for (int k = 0; k < C; ++k) acc[k] = dd::warp_sum(acc[k]);
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < C; ++k) s_db[warp - 1][k] = acc[k];
-      }
-    }
-  } else if (warp < 4) {
-    // =========================== producers (stride 2: warps 0..3, cp.async) ======================
-    uint32_t n = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
-      const int h0 = hs * WG_ROWS, w0 = wt * TILE_M;
-      const uint32_t stage = n % G::NST;
-      umma::mbar_wait(&bars->empty[stage], ((n / G::NST) & 1) ^ 1);
-      const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
-      const uint32_t ds = xs + WG_X_BYTES;
-      const __nv_bfloat16* ximg = x + (size_t)b * H * W * C;
-      const __nv_bfloat16* dimg = dy + (size_t)b * Ho * Wo * C;
-#pragma unroll
-      for (int r = 0; r < WG_XROWS; ++r) {
-        const int row = h0 * STRIDE - 1 + r;
-        const bool row_ok = row >= 0 && row < H;
-        load_slab<G::XPIX, STRIDE == 2 ? G::XROWS_ALLOC * 4 : 0>(xs + (r * 4) * PS, ximg + (size_t)(row_ok ? row : 0) * W * C,
-                                                                 row_ok, w0 * STRIDE - 1, W, tid);
-      }
-#pragma unroll
-      for (int r = 0; r < WG_ROWS; ++r) {
-        const int row = h0 + r;
-        const bool row_ok = row < Ho;
-        load_slab<TILE_M, 0, PSD>(ds + (r * 4) * PSD, dimg + (size_t)(row_ok ? row : 0) * Wo * C, row_ok, w0, Wo, tid);
-      }
-      umma::cp_async_mbar_arrive_noinc(&bars->full[stage]);     // published when this thread's copies land
-    }
-  } else {
-    // =========================== MMA issuer (warp 4: whole warp loops, elected lane issues) =====
-    constexpr uint32_t idesc = umma::make_idesc_bf16(128, G::N, true, true);
-    uint32_t n = 0;
-    uint32_t fresh = 1;     // accumulators not yet written
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const uint32_t stage = n % G::NST;
-      umma::mbar_wait(&bars->full[stage], (n / G::NST) & 1);
-      if (STRIDE != 1) umma::fence_proxy_async_smem();     // cp.async writes (generic proxy); TMA writes need no fence
-      umma::tc_fence_after_sync();
-      const uint32_t xs = umma::smem_u32(smem + stage * WG_STAGE_BYTES);
-      const uint32_t x_lo = umma::desc_lo(xs, 128), d_lo = umma::desc_lo(xs + WG_X_BYTES, 128);
-      constexpr uint32_t x_hi = umma::desc_hi(PS), d_hi = umma::desc_hi(PSD);
-      if (umma::elect_one())
-#pragma unroll
-      for (int p = 0; p < (STRIDE == 1 ? WG_ROWS / 2 : 1); ++p) {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          // stride 1: x column w+kw-1 = slab index (w-w0)+kw.  stride 2: kw 0 -> even[i], 1 -> odd[i], 2 -> even[i+1]
-          const uint32_t a_off = STRIDE == 1 ? (2 * p * 4) * PS + kw * 16
-                                             : (kw == 1 ? G::XROWS_ALLOC * 4 * PS : 0) + (kw == 2 ? 16 : 0);
-#pragma unroll
-          for (int ks = 0; ks < TILE_M / 16; ++ks)
-            umma::mma_bf16_lohi(tmem + kw * 64, x_lo + ((a_off + ks * 256) >> 4), x_hi,
-                                d_lo + (((2 * p * 4) * PSD + ks * 256) >> 4), d_hi, idesc,
-                                (fresh && p == 0 && ks == 0) ? 0u : 1u);
-        }
-      }
-      fresh = 0;
-      if (umma::elect_one()) umma::mma_commit(&bars->empty[stage]);
-      __syncwarp();
-    }
-    if (umma::elect_one()) umma::mma_commit(&bars->done);
-  }
-  // =========================== epilogue: TMEM -> per-CTA partials (warps 0..3) ===================
-  __syncwarp();
-  if (warp < 4) {
-    mbar_wait_relaxed(&bars->done, 0);
-    umma::tc_fence_after_sync();
-    const int r = warp;                      // TMEM lane quarter = x row offset r; lane = ci
-    float* out = partial + (size_t)blockIdx.x * WG_PARTIAL;
-#pragma unroll 1
-    for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll 1
-      for (int q = 0; q < G::NQ; ++q) {
-        uint32_t v[32];
-        umma::tmem_ld_32x32(tmem + ((uint32_t)(r * 32) << 16) + kw * 64 + q * 32, v);
-        umma::tmem_ld_wait();
-        const int kh = r - q;
-        if (kh >= 0 && kh <= 2) {
-          float4* dst = reinterpret_cast<float4*>(out + (size_t)q * 9 * C * C + ((kh * 3 + kw) * C + lane) * C);
-#pragma unroll
-          for (int g4 = 0; g4 < 8; ++g4)
-            dst[g4] = make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]),
-                                  __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
-        }
-      }
-    }
-  }
-  umma::tc_fence_before_sync();
-  __syncthreads();
-  if (STRIDE == 1 && tid < C) db_partial[(size_t)blockIdx.x * C + tid] = s_db[0][tid] + s_db[1][tid];
-  if (warp == 4) umma::tmem_dealloc(tmem, 256);
-}
-
-// per-channel sums of an NHWC bf16 tensor (bias gradient): partial[blk][32]
-__global__ void __launch_bounds__(256) colsum_nhwc_bf16_kernel(const __nv_bfloat16* __restrict__ dy, long long npix,
-                                                               float* __restrict__ partial) {
-  __shared__ float red[64][33];
-  const int cg = threadIdx.x & 3, pl = threadIdx.x >> 2;     // 64 pixel lanes x 4 channel groups
-  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long p = (long long)blockIdx.x * 64 + pl; p < npix; p += (long long)gridDim.x * 64) {
-    float v[8];
-    dd::ld8<__nv_bfloat16>(dy + p * C + cg * 8, v);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s[k] += v[k];
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) red[pl][cg * 8 + k] = s[k];
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float t = 0.f;
-    for (int i = 0; i < 64; ++i) t += red[i][threadIdx.x];
-    partial[(size_t)blockIdx.x * C + threadIdx.x] = t;
-  }
-}
-
-// dw[co][ci][tap] = sum over CTAs and their q slots (nslots = CTAs x NQ); db[co] = sum over colsum CTAs
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nslots, const float* __restrict__ dbp,
-                                       int ndb, float* __restrict__ dw, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 9 * C * C) {
-    float s = 0.f;
-    for (int blk = 0; blk < nslots; ++blk) s += partial[(size_t)blk * (9 * C * C) + i];
-    const int co = i & 31, ci = (i >> 5) & 31, tap = i >> 10;
-    dw[(co * C + ci) * 9 + tap] = s;
-  } else if (i < 9 * C * C + C) {
-    const int co = i - 9 * C * C;
-    float s = 0.f;
-    for (int blk = 0; blk < ndb; ++blk) s += dbp[(size_t)blk * C + co];
-    db[co] = s;
-  }
-}
-
-constexpr int kDbBlocks = dd::kSMs * 4;
-
 
 // ================================================================================================
 // First encoder conv (3 -> 32, components.py:19,41) on the tensor cores, stitch folded in.
@@ -1489,42 +1230,6 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
   return fail(DD_ERR_UNSUPPORTED, "conv_tc: mode %d stride %d", mode, stride);
 }
 
-template <int STRIDE>
-static int wgrad_tc_launch(const void* x, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int B, int H,
-                           int W, cudaStream_t st) {
-  using G = WgGeo<STRIDE>;
-  const int Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
-  const int items = B * ((Wo + TILE_M - 1) / TILE_M) * ((Ho + G::ROWS - 1) / G::ROWS);
-  const int grid = items < kSMs ? items : kSMs;
-  const size_t need = ((size_t)grid * G::PARTIAL + (size_t)kDbBlocks * C) * sizeof(float);
-  if (ws_bytes < need) return fail(DD_ERR_WORKSPACE, "tcgen05 wgrad: workspace %zu < %zu", ws_bytes, need);
-  float* partial = (float*)ws;
-  float* dbp = partial + (size_t)grid * G::PARTIAL;
-  auto k = conv3x3_c32_wgrad_tc_kernel<STRIDE>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-  if (e != cudaSuccess) return fail((int)e, "wgrad_tc: cudaFuncSetAttribute(%d): %s", G::SMEM, cudaGetErrorString(e));
-  CUtensorMap mx = {}, mdy = {};
-  if (STRIDE == 1) {
-    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0)
-      return fail(DD_ERR_ALIGNMENT, "tcgen05 wgrad: x / dy are not 16-byte aligned");
-    if (int r = tma_map_nhwc_c8(&mx, x, (uint64_t)B, (uint64_t)H, (uint64_t)W, G::XPIX))
-      return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: cuTensorMapEncodeTiled(x) -> %d", r);
-    if (int r = tma_map_nhwc_c8(&mdy, dy, (uint64_t)B, (uint64_t)Ho, (uint64_t)Wo, TILE_M))
-      return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: cuTensorMapEncodeTiled(dy) -> %d", r);
-  }
-  k<<<grid, WG_THREADS, G::SMEM, st>>>(mx, mdy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, dbp, B, H, W, Ho, Wo);
-  if (int err = check_launch("conv3x3_c32_wgrad_tc")) return err;
-  int dbg = grid;                       // stride 1: the weight-gradient kernel wrote one db partial per CTA
-  if (STRIDE != 1) {
-    const long long npix = (long long)B * Ho * Wo;
-    dbg = (int)((npix + 63) / 64 < kDbBlocks ? (npix + 63) / 64 : kDbBlocks);
-    colsum_nhwc_bf16_kernel<<<dbg, 256, 0, st>>>((const __nv_bfloat16*)dy, npix, dbp);
-    if (int err = check_launch("colsum_nhwc_bf16")) return err;
-  }
-  wgrad_tc_reduce_kernel<<<(9 * C * C + C + 255) / 256, 256, 0, st>>>(partial, grid * G::NQ, dbp, dbg, dw, db);
-  return check_launch("wgrad_tc_reduce");
-}
-
 int conv_c1_fwd_tc(const float* in, int in_is_views, const float* w, const float* bias, void* out, int B, int H, int Wm,
                    cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(out) & 31) != 0) return fail(DD_ERR_ALIGNMENT, "conv_c1_tc: out %p is not 32-byte aligned", out);
@@ -1554,13 +1259,6 @@ int conv_c1_wgrad_tc(const float* in, int in_is_views, const void* dy, float* dw
   if (int err = in_is_views ? launch1(conv_c1_wgrad_tc_kernel<true>) : launch1(conv_c1_wgrad_tc_kernel<false>)) return err;
   c1_wgrad_tc_reduce_kernel<<<30, 256, 0, st>>>((const float*)ws, grid * CW_RB, dw, db);
   return check_launch("c1_wgrad_tc_reduce");
-}
-
-int conv3x3_c32_wgrad_tc(const void* x, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int B, int H,
-                         int W, int stride, cudaStream_t st) {
-  if (stride == 1) return wgrad_tc_launch<1>(x, dy, dw, db, ws, ws_bytes, B, H, W, st);
-  if (stride == 2) return wgrad_tc_launch<2>(x, dy, dw, db, ws, ws_bytes, B, H, W, st);
-  return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: stride %d", stride);
 }
 
 }  // namespace dd

@@ -355,7 +355,7 @@ def test_bce_threat_forward_backward(dd, shape, u8):
     ld = logits.cuda().requires_grad_(True)
     loss, probs, binary, stats, counts = dd.bce_threat(ld, target_b.cuda() if u8 else target.cuda())
     assert abs(float(loss) - float(ref["loss"])) < 1e-6 * max(1.0, abs(float(ref["loss"])))
-    assert rel_max_err(probs, ref["probs"]) < 2e-7                       # IEEE sigmoid: a last place or two
+    assert rel_max_err(probs, ref["probs"]) < 3e-7                       # IEEE sigmoid: a last place or two of 0.5
     assert torch.equal(binary.cpu().float(), ref["binary"])             # bit-exact binarisation
     # forward()'s contract (roadmap_bce_v2.py:72,81,140): rounding the RETURNED probabilities gives the binary map
     assert torch.equal(probs.round(), binary.float())
