@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
 
 DD_F32, DD_BF16 = 0, 1
+IN_VIEWS, IN_U8 = 1, 2          # dd_conv_c1_* in_flags
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
 _P, _I, _L, _Z, _F = c_void_p, c_int, c_longlong, c_size_t, c_float

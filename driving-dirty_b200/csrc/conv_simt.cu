@@ -515,9 +515,9 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
 int conv3x3_c32_wgrad_tc(const void* x, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int B,
                          int H, int W, int stride, cudaStream_t st);
 bool conv_tc_supported(int H, int W, int stride, int mode);
-int conv_c1_fwd_tc(const float* in, int in_is_views, const float* w, const float* bias, void* out, int B, int H, int Wm,
+int conv_c1_fwd_tc(const void* in, int in_flags, const float* w, const float* bias, void* out, int B, int H, int Wm,
                    cudaStream_t st);
-int conv_c1_wgrad_tc(const float* in, int in_is_views, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes,
+int conv_c1_wgrad_tc(const void* in, int in_flags, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes,
                      int B, int H, int Wm, cudaStream_t st);
 }  // namespace dd
 
@@ -586,15 +586,20 @@ extern "C" int dd_conv3x3_c32_wgrad(const void* x, const void* dy, float* dw, fl
   return dd::fail(DD_ERR_UNSUPPORTED, "dd_conv3x3_c32_wgrad: dtype %d", dtype);
 }
 
-extern "C" int dd_conv_c1_fwd(const float* in, int in_is_views, const float* w_oihw, const float* bias, void* out,
+extern "C" int dd_conv_c1_fwd(const void* in_, int in_flags, const float* w_oihw, const float* bias, void* out,
                               int out_dtype, int B, int H, int Wm, int impl, void* stream) {
-  DD_REQUIRE(in && w_oihw && bias && out, DD_ERR_BAD_ARG, "dd_conv_c1_fwd: null pointer");
+  DD_REQUIRE(in_ && w_oihw && bias && out, DD_ERR_BAD_ARG, "dd_conv_c1_fwd: null pointer");
   DD_REQUIRE(B >= 0 && H > 0 && Wm > 0, DD_ERR_BAD_ARG, "dd_conv_c1_fwd: bad shape");
+  DD_REQUIRE((in_flags & ~3) == 0, DD_ERR_BAD_ARG, "dd_conv_c1_fwd: in_flags %d", in_flags);
+  const int in_is_views = in_flags & DD_IN_VIEWS;
   DD_REQUIRE(!in_is_views || Wm % 6 == 0, DD_ERR_BAD_ARG, "dd_conv_c1_fwd: mosaic width %d not a multiple of 6", Wm);
   if (B == 0) return 0;
   cudaStream_t st = dd::as_stream(stream);
   DD_REQUIRE(!(out_dtype == DD_F32 && impl == DD_IMPL_TCGEN05), DD_ERR_UNSUPPORTED, "tcgen05 conv is bf16 only");
-  if (out_dtype == DD_BF16 && impl != DD_IMPL_SIMT) return dd::conv_c1_fwd_tc(in, in_is_views, w_oihw, bias, out, B, H, Wm, st);
+  if (out_dtype == DD_BF16 && impl != DD_IMPL_SIMT) return dd::conv_c1_fwd_tc(in_, in_flags, w_oihw, bias, out, B, H, Wm, st);
+  DD_REQUIRE(!(in_flags & DD_IN_U8), DD_ERR_UNSUPPORTED, "dd_conv_c1_fwd: raw-byte input runs on the bf16 tensor-core path only "
+             "(fp32 parity path: dd_stitch_u8 first)");
+  const float* in = (const float*)in_;
   dim3 grid((Wm + 31) / 32, (H + 7) / 8, B);
   if (out_dtype == DD_F32) {
     if (in_is_views) conv_c1_fwd_simt<float, true><<<grid, 256, 0, st>>>(in, w_oihw, bias, (float*)out, H, Wm);
@@ -608,16 +613,20 @@ extern "C" int dd_conv_c1_fwd(const float* in, int in_is_views, const float* w_o
   return dd::check_launch("conv_c1_fwd");
 }
 
-extern "C" int dd_conv_c1_wgrad(const float* in, int in_is_views, const void* dy, int dtype, float* dw, float* db,
+extern "C" int dd_conv_c1_wgrad(const void* in_, int in_flags, const void* dy, int dtype, float* dw, float* db,
                                 void* workspace, size_t ws_bytes, int B, int H, int Wm, int impl, void* stream) {
-  DD_REQUIRE(in && dy && dw && db && workspace, DD_ERR_BAD_ARG, "dd_conv_c1_wgrad: null pointer");
+  DD_REQUIRE(in_ && dy && dw && db && workspace, DD_ERR_BAD_ARG, "dd_conv_c1_wgrad: null pointer");
+  DD_REQUIRE((in_flags & ~3) == 0, DD_ERR_BAD_ARG, "dd_conv_c1_wgrad: in_flags %d", in_flags);
+  const int in_is_views = in_flags & DD_IN_VIEWS;
   DD_REQUIRE(B > 0 && H > 0 && Wm > 0, DD_ERR_BAD_ARG, "dd_conv_c1_wgrad: bad shape");
   DD_REQUIRE(ws_bytes >= kWgradWsBytes, DD_ERR_WORKSPACE, "dd_conv_c1_wgrad: workspace too small");
   cudaStream_t st = dd::as_stream(stream);
   DD_REQUIRE(!(dtype == DD_F32 && impl == DD_IMPL_TCGEN05), DD_ERR_UNSUPPORTED, "tcgen05 conv is bf16 only");
   DD_REQUIRE(!in_is_views || Wm % 6 == 0, DD_ERR_BAD_ARG, "dd_conv_c1_wgrad: mosaic width %d not a multiple of 6", Wm);
   if (dtype == DD_BF16 && impl != DD_IMPL_SIMT)
-    return dd::conv_c1_wgrad_tc(in, in_is_views, dy, dw, db, workspace, ws_bytes, B, H, Wm, st);
+    return dd::conv_c1_wgrad_tc(in_, in_flags, dy, dw, db, workspace, ws_bytes, B, H, Wm, st);
+  DD_REQUIRE(!(in_flags & DD_IN_U8), DD_ERR_UNSUPPORTED, "dd_conv_c1_wgrad: raw-byte input runs on the bf16 tensor-core path only");
+  const float* in = (const float*)in_;
   const int tiles = B * ((H + 7) / 8) * ((Wm + 31) / 32);
   const int nblk = tiles < kWgradBlocks ? tiles : kWgradBlocks;
   float* ws = (float*)workspace;

@@ -323,9 +323,8 @@ constexpr int S1_RING = 4 * S1_NQUAD;
 constexpr int S1_NACC = 16;         // accumulator ring: 16 x 32 TMEM columns, in 4 groups of 4 rows
 constexpr int S1_NGRP = S1_NACC / 4;
 constexpr int S1_EPI = 8;           // epilogue warps
-constexpr int S1_PS = PS;            // plane stride 2176 B = 17 x 128 (TMA destinations are 128-byte aligned); a box fills 2080 B
-constexpr int S1_SLAB = 4 * S1_PS;
-constexpr int S1_SLAB_TX = 4 * 130 * 16;   // bytes one input row's four boxes deliver
+constexpr int S1_SLAB = 17 * 512;   // one input row = ONE whole-pixel TMA box [130 px][32 ch] (8320 B), pitch rounded up to the 512-byte swizzle period
+constexpr int S1_SLAB_TX = 130 * 64;       // bytes one input row's box delivers
 constexpr int S1_WN = 96 * 16;      // bytes per (kw, channel group) weight block: [3 kh slots x 32 co][8 ci]
 constexpr int S1_SMEM = W_BYTES + S1_RING * S1_SLAB + 1024;
 constexpr int S1_THREADS = 32 * (NPROD + 1 + S1_EPI);
@@ -391,9 +390,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
     // =========================== producer: one thread of warp 0, TMA (warps 1..3 idle) ============
     // cp.async (LDGSTS) tops out near 25-30 KB in flight per SM (every conv kernel fed that way sat at 35-50 % of
     // HBM bandwidth with its producer warps stalled issuing copies); TMA takes a whole input row per instruction
-    // group and keeps the full ring in flight.  Four boxes per row (one per channel group: [130 px][8 ch] planes);
+    // and keeps the full ring in flight.  ONE box of whole pixels per row ([130 px][32 ch], 64-byte swizzle: the K-major
+    // SWIZZLE_64B operand layout; round 1's four [130 px][8 ch] boxes read half sectors from L2, four requests per row);
     // coordinates outside the image are zero-filled by the TMA unit = the conv padding.  One mbarrier per quad of
-    // rows: expect_tx for the 16 boxes, then the loads.
+    // rows: expect_tx for the 4 boxes, then the loads.
     if (warp == 0 && lane == 0) {
       umma::tma_prefetch_desc(&map_in);
       uint32_t g = 0;
@@ -412,9 +412,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
             const int left = last_item ? rows + 2 - s : 4;
             umma::mbar_expect_tx(full, (uint32_t)(min(left, 4) * S1_SLAB_TX));
           }
-          const uint32_t dst = umma::smem_u32(s_slab + (g % S1_RING) * S1_SLAB);
-#pragma unroll
-          for (int cg = 0; cg < 4; ++cg) umma::tma_load_4d(dst + cg * S1_PS, &map_in, cg * 8, c0, h0 - 1 + s, b, full);
+          umma::tma_load_4d(umma::smem_u32(s_slab + (g % S1_RING) * S1_SLAB), &map_in, 0, c0, h0 - 1 + s, b, full);
         }
       }
     }
@@ -422,8 +420,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
     // =========================== MMA issuer (whole warp loops, elected lane issues) ===============
     constexpr uint32_t idesc32 = umma::make_idesc_bf16(TILE_M, 32, false, false);
     constexpr uint32_t IDESC_NSTEP = (32u >> 3) << 17;                        // +32 columns of N
-    constexpr uint32_t ab_hi = umma::desc_hi(128);
-    const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), S1_PS);      // A: LBO = plane stride, SBO = 128
+    constexpr uint32_t b_hi = umma::desc_hi(128);
+    constexpr uint32_t a_hi = umma::desc_hi_sw64(512);                        // A: K-major SWIZZLE_64B, SBO = 8 pixels x 64 B
+    const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), 0);          // (LBO unused: one swizzle span covers K = 32)
     const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), S1_WN);         // B: LBO = channel-group block, SBO = 128
     uint32_t g = 0;             // slab counter
     uint32_t rc0 = 0;           // output-row counter at the start of the item (accumulator ring position)
@@ -465,29 +464,29 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
             const uint32_t sl = rc_done % S1_NACC;
             const uint32_t d0 = tmem + sl * 32;
             constexpr uint32_t i32 = idesc32, i64 = idesc32 + IDESC_NSTEP, i96 = idesc32 + 2 * IDESC_NSTEP;
-#define S1_AT(t) (slab_lo + (((((t) >> 1) * 16) + (2 * ((t) & 1)) * S1_PS) >> 4))
+#define S1_AT(t) (slab_lo + (((((t) >> 1) * 64) + ((t) & 1) * 32) >> 4))      /* tap kw = t >> 1: +kw pixels; K half: +32 B */
 #define S1_BT(t) (b_lo0 + ((((((t) >> 1) * 4) + 2 * ((t) & 1)) * S1_WN) >> 4))
             if (sl <= S1_NACC - 3) {
-              umma::mma_bf16_lohi(d0, S1_AT(0), ab_hi, S1_BT(0), ab_hi, i64, 1u);
-              umma::mma_bf16_lohi(d0 + 64, S1_AT(0), ab_hi, S1_BT(0) + 64, ab_hi, i32, 0u);
+              umma::mma_bf16_lohi(d0, S1_AT(0), a_hi, S1_BT(0), b_hi, i64, 1u);
+              umma::mma_bf16_lohi(d0 + 64, S1_AT(0), a_hi, S1_BT(0) + 64, b_hi, i32, 0u);
 #pragma unroll
-              for (int t = 1; t < 6; ++t) umma::mma_bf16_lohi(d0, S1_AT(t), ab_hi, S1_BT(t), ab_hi, i96, 1u);
+              for (int t = 1; t < 6; ++t) umma::mma_bf16_lohi(d0, S1_AT(t), a_hi, S1_BT(t), b_hi, i96, 1u);
             } else if (sl == S1_NACC - 2) {               // newest row wraps to slot 0
-              umma::mma_bf16_lohi(d0, S1_AT(0), ab_hi, S1_BT(0), ab_hi, i64, 1u);
-              umma::mma_bf16_lohi(tmem, S1_AT(0), ab_hi, S1_BT(0) + 64, ab_hi, i32, 0u);
+              umma::mma_bf16_lohi(d0, S1_AT(0), a_hi, S1_BT(0), b_hi, i64, 1u);
+              umma::mma_bf16_lohi(tmem, S1_AT(0), a_hi, S1_BT(0) + 64, b_hi, i32, 0u);
 #pragma unroll
               for (int t = 1; t < 6; ++t) {
-                umma::mma_bf16_lohi(d0, S1_AT(t), ab_hi, S1_BT(t), ab_hi, i64, 1u);
-                umma::mma_bf16_lohi(tmem, S1_AT(t), ab_hi, S1_BT(t) + 64, ab_hi, i32, 1u);
+                umma::mma_bf16_lohi(d0, S1_AT(t), a_hi, S1_BT(t), b_hi, i64, 1u);
+                umma::mma_bf16_lohi(tmem, S1_AT(t), a_hi, S1_BT(t) + 64, b_hi, i32, 1u);
               }
             } else {                                      // slots 15, 0, 1
-              umma::mma_bf16_lohi(d0, S1_AT(0), ab_hi, S1_BT(0), ab_hi, i32, 1u);
-              umma::mma_bf16_lohi(tmem, S1_AT(0), ab_hi, S1_BT(0) + 32, ab_hi, i32, 1u);
-              umma::mma_bf16_lohi(tmem + 32, S1_AT(0), ab_hi, S1_BT(0) + 64, ab_hi, i32, 0u);
+              umma::mma_bf16_lohi(d0, S1_AT(0), a_hi, S1_BT(0), b_hi, i32, 1u);
+              umma::mma_bf16_lohi(tmem, S1_AT(0), a_hi, S1_BT(0) + 32, b_hi, i32, 1u);
+              umma::mma_bf16_lohi(tmem + 32, S1_AT(0), a_hi, S1_BT(0) + 64, b_hi, i32, 0u);
 #pragma unroll
               for (int t = 1; t < 6; ++t) {
-                umma::mma_bf16_lohi(d0, S1_AT(t), ab_hi, S1_BT(t), ab_hi, i32, 1u);
-                umma::mma_bf16_lohi(tmem, S1_AT(t), ab_hi, S1_BT(t) + 32, ab_hi, i64, 1u);
+                umma::mma_bf16_lohi(d0, S1_AT(t), a_hi, S1_BT(t), b_hi, i32, 1u);
+                umma::mma_bf16_lohi(tmem, S1_AT(t), a_hi, S1_BT(t) + 32, b_hi, i64, 1u);
               }
             }
           } else {
@@ -504,14 +503,14 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
             const int no = is_new ? n - 1 : n;                // rows that already hold partial sums
             const int no1 = min(no, n1), no2 = no - no1;
             // (kw 0, K half 0): accumulate into the older rows, overwrite the newest
-            if (no1 > 0) umma::mma_bf16_lohi(d0, slab_lo, ab_hi, b_lo0 + bo0, ab_hi, idesc32 + (no1 - 1) * IDESC_NSTEP, 1u);
-            if (no2 > 0) umma::mma_bf16_lohi(tmem, slab_lo, ab_hi, b_lo0 + bo1, ab_hi, idesc32 + (no2 - 1) * IDESC_NSTEP, 1u);
+            if (no1 > 0) umma::mma_bf16_lohi(d0, slab_lo, a_hi, b_lo0 + bo0, b_hi, idesc32 + (no1 - 1) * IDESC_NSTEP, 1u);
+            if (no2 > 0) umma::mma_bf16_lohi(tmem, slab_lo, a_hi, b_lo0 + bo1, b_hi, idesc32 + (no2 - 1) * IDESC_NSTEP, 1u);
             if (is_new)
-              umma::mma_bf16_lohi(tmem + ((rc0 + jhi) % S1_NACC) * 32, slab_lo, ab_hi, b_lo0 + (blk + n - 1) * 32, ab_hi, idesc32, 0u);
+              umma::mma_bf16_lohi(tmem + ((rc0 + jhi) % S1_NACC) * 32, slab_lo, a_hi, b_lo0 + (blk + n - 1) * 32, b_hi, idesc32, 0u);
 #pragma unroll
             for (int t = 1; t < 6; ++t) {
-              umma::mma_bf16_lohi(d0, S1_AT(t), ab_hi, S1_BT(t) + bo0, ab_hi, i0, 1u);
-              if (two) umma::mma_bf16_lohi(tmem, S1_AT(t), ab_hi, S1_BT(t) + bo1, ab_hi, i1, 1u);
+              umma::mma_bf16_lohi(d0, S1_AT(t), a_hi, S1_BT(t) + bo0, b_hi, i0, 1u);
+              if (two) umma::mma_bf16_lohi(tmem, S1_AT(t), a_hi, S1_BT(t) + bo1, b_hi, i1, 1u);
             }
           }
 #undef S1_AT
@@ -632,7 +631,7 @@ int launch_s1(const void* in, const float* w, const float* bias, const void* mas
   static const int dbg = getenv("DD_CONV_DBG") ? atoi(getenv("DD_CONV_DBG")) : 0;   // profiling aid: 1 no MMA, 2 no stores
   if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return dd::fail(DD_ERR_ALIGNMENT, "conv_tc s1: input is not 16-byte aligned");
   CUtensorMap map;
-  if (int r = dd::tma_map_nhwc_c8(&map, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, 130))
+  if (int r = dd::tma_map_nhwc_sw64(&map, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, 130))
     return dd::fail(DD_ERR_UNSUPPORTED, "conv_tc s1: cuTensorMapEncodeTiled -> %d (B %d H %d W %d)", r, B, H, W);
   k<<<grid, S1_THREADS, S1_SMEM, st>>>(map, w, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H, W, dbg);
   return dd::check_launch("conv3x3_c32_s1_tc");
@@ -816,18 +815,7 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
   if (warp == MMA_WARP) umma::tmem_dealloc(tmem, 256);
 }
 
-// ================================================================================================
-// The weight gradients of c2 / c3 live in conv_wgrad_tc.cu (rolling row ring, whole-pixel TMA boxes).
-// Shared pieces of the c1 weight-gradient kernel below:
-// ================================================================================================
-constexpr int PSD = TILE_M * 16;                 // dy plane stride (128 pixels)
-
-struct WgBars {
-  uint64_t full[4], empty[4], done;
-  uint32_t tmem_base;
-};
-
-constexpr int WG_THREADS = 160;
+// (the weight gradients of c1 / c2 / c3 live in conv_wgrad_tc.cu: rolling row rings fed by whole-pixel TMA boxes)
 
 // ================================================================================================
 // First encoder conv (3 -> 32, components.py:19,41) on the tensor cores, stitch folded in.
@@ -850,9 +838,14 @@ struct C1Bars {
 };
 
 // pointer to channel 0 of (b, mosaic row h, mosaic column wm); channel stride returned in cstride
-template <bool IS_VIEWS>
-__device__ __forceinline__ const float* c1_src(const float* __restrict__ in, int b, int h, int wm, int H, int Wm,
-                                               size_t& cstride) {
+template <typename TIN> __device__ __forceinline__ float c1_ld(const TIN* p);
+template <> __device__ __forceinline__ float c1_ld<float>(const float* p) { return __ldg(p); }
+// torchvision ToTensor (data_helper.py:109-114): byte -> float32, divided by 255 (IEEE division: bit-identical)
+template <> __device__ __forceinline__ float c1_ld<uint8_t>(const uint8_t* p) { return __fdiv_rn((float)__ldg(p), 255.0f); }
+
+template <bool IS_VIEWS, typename TIN>
+__device__ __forceinline__ const TIN* c1_src(const TIN* __restrict__ in, int b, int h, int wm, int H, int Wm,
+                                             size_t& cstride) {
   if (IS_VIEWS) {
     const int W = Wm / 6;
     const int j = wm / W, w = wm - j * W;
@@ -864,8 +857,8 @@ __device__ __forceinline__ const float* c1_src(const float* __restrict__ in, int
 }
 
 // one input row -> [pixel][8 ch] bf16 plane (130 pixels), by one warp
-template <bool IS_VIEWS>
-__device__ __forceinline__ void c1_load_row(uint8_t* __restrict__ slab, const float* __restrict__ in, int b, int r, int c0,
+template <bool IS_VIEWS, typename TIN>
+__device__ __forceinline__ void c1_load_row(uint8_t* __restrict__ slab, const TIN* __restrict__ in, int b, int r, int c0,
                                             int H, int Wm, int lane) {
   float v[5][3];
   bool ok[5];
@@ -875,8 +868,8 @@ __device__ __forceinline__ void c1_load_row(uint8_t* __restrict__ slab, const fl
     ok[k] = li < 130 && r >= 0 && r < H && col >= 0 && col < Wm;
     if (ok[k]) {
       size_t cs;
-      const float* p = c1_src<IS_VIEWS>(in, b, r, col, H, Wm, cs);
-      v[k][0] = __ldg(p); v[k][1] = __ldg(p + cs); v[k][2] = __ldg(p + 2 * cs);
+      const TIN* p = c1_src<IS_VIEWS, TIN>(in, b, r, col, H, Wm, cs);
+      v[k][0] = c1_ld<TIN>(p); v[k][1] = c1_ld<TIN>(p + cs); v[k][2] = c1_ld<TIN>(p + 2 * cs);
     } else {
       v[k][0] = v[k][1] = v[k][2] = 0.f;
     }
@@ -894,8 +887,8 @@ __device__ __forceinline__ void c1_load_row(uint8_t* __restrict__ slab, const fl
   }
 }
 
-template <bool IS_VIEWS>
-__global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const float* __restrict__ in,
+template <bool IS_VIEWS, typename TIN>
+__global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __restrict__ in,
                                                                     const float* __restrict__ w_oihw,
                                                                     const float* __restrict__ bias,
                                                                     __nv_bfloat16* __restrict__ out, int B, int H, int Wm) {
@@ -942,7 +935,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const float* 
         if ((g % C1_NPROD) != (uint32_t)warp) continue;
         const uint32_t slot = g % C1_RING;
         umma::mbar_wait(&bars->empty[slot], ((g / C1_RING) & 1) ^ 1);
-        c1_load_row<IS_VIEWS>(s_slab + slot * PS, in, b, h0 - 1 + sidx, wt * TILE_M - 1, H, Wm, lane);
+        c1_load_row<IS_VIEWS, TIN>(s_slab + slot * PS, in, b, h0 - 1 + sidx, wt * TILE_M - 1, H, Wm, lane);
         umma::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(&bars->full[slot]);
@@ -1016,177 +1009,6 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const float* 
 }
 
 
-// ================================================================================================
-// Weight gradient of the first conv (3 -> 32) on the tensor cores, stitch folded in.
-//   dW[co][c][kh][kw] = sum_{b,h,w} in[b,c,h+kh-1,w+kw-1] * dy[b,h,w,co],   db[co] = sum dy[b,h,w,co]
-// The contraction runs over pixels (both operands MN-major, K = 16 pixels per tcgen05.mma).  The
-// producers convert the fp32 input into "tap-packed" planes: per x row two 8-channel chunks per
-// pixel p, channel j = kw*3 + c (j < 9) = in[c][p + kw - 1], j = 9 = 1.0 (-> bias gradient), rest 0,
-// so the three horizontal taps ride in the M dimension instead of costing three MMAs.
-// Work item = 128-pixel strip x 6 dy rows: A = 8 x rows x 16 channels (M = 128), B = 6 dy rows x 32 co
-// (N = 192); block (r, q) of D is tap kh = r - q, every x row is used (18 of the 48 blocks are
-// taps, the rest is ignored).  One TMEM accumulator per CTA over all its items, written once.
-// ================================================================================================
-constexpr int CW_RB = 6, CW_XR = 8;
-constexpr int CW_X_BYTES = CW_XR * 2 * PSD;            // [x row][half][128 px][8 ch]
-constexpr int CW_DY_BYTES = CW_RB * 4 * PSD;           // [dy row][cg][128 px][8 co]
-constexpr int CW_STAGE = CW_X_BYTES + CW_DY_BYTES;     // 80 KB
-constexpr int CW_SMEM = 2 * CW_STAGE + 1024;
-constexpr int CW_PARTIAL = CW_RB * 3 * 10 * C;         // floats per CTA: [q][kh][j][co]
-
-template <bool IS_VIEWS>
-__global__ void __launch_bounds__(WG_THREADS, 1) conv_c1_wgrad_tc_kernel(const float* __restrict__ in,
-                                                                          const __nv_bfloat16* __restrict__ dy,
-                                                                          float* __restrict__ partial, int B, int H,
-                                                                          int Wm) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  WgBars* bars = reinterpret_cast<WgBars*>(smem + 2 * CW_STAGE);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int wtiles = (Wm + TILE_M - 1) / TILE_M;
-  const int hsegs = (H + CW_RB - 1) / CW_RB;
-  const int items = B * wtiles * hsegs;
-
-  if (tid == 0) {
-    // per stage: 128 plain arrivals (x planes written, fenced) + 128 cp.async arrivals (dy landed)
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->full[i], 256); umma::mbar_init(&bars->empty[i], 1); }
-    umma::mbar_init(&bars->done, 1);
-    umma::fence_mbar_init();
-  }
-  if (warp == 4) umma::tmem_alloc(&bars->tmem_base, 256);
-  umma::tc_fence_before_sync();
-  __syncthreads();
-  umma::tc_fence_after_sync();
-  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
-
-  if (warp < 4) {
-    // =========================== producers: thread = pixel of the strip ==========================
-    const int Wv = IS_VIEWS ? Wm / 6 : Wm;
-    const size_t cstride = (size_t)H * Wv;
-    uint32_t n = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
-      const int h0 = hs * CW_RB, w0 = wt * TILE_M;
-      const uint32_t stage = n & 1;
-      umma::mbar_wait(&bars->empty[stage], ((n >> 1) & 1) ^ 1);
-      uint8_t* xs = smem + stage * CW_STAGE;
-      const uint32_t ds = umma::smem_u32(xs) + CW_X_BYTES;
-      const __nv_bfloat16* dimg = dy + (size_t)b * H * Wm * C;
-#pragma unroll
-      for (int q = 0; q < CW_RB; ++q) {
-        const int row = h0 + q;
-        const bool row_ok = row < H;
-        load_slab<TILE_M, 0, PSD>(ds + (q * 4) * PSD, dimg + (size_t)(row_ok ? row : 0) * Wm * C, row_ok, w0, Wm, tid);
-      }
-      umma::cp_async_mbar_arrive_noinc(&bars->full[stage]);
-      // columns w0+tid-1 .. w0+tid+1: offset of channel 0, row 0 (views: through the mosaic slot map)
-      size_t off[3];
-      bool cok[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const int col = w0 + tid + d - 1;
-        cok[d] = col >= 0 && col < Wm;
-        const int cc = cok[d] ? col : 0;
-        if (IS_VIEWS) {
-          const int j = cc / Wv, w = cc - j * Wv;
-          off[d] = (((size_t)b * 6 + dd::view_of_slot(j)) * 3) * cstride + w;
-        } else {
-          off[d] = ((size_t)b * 3) * cstride + cc;
-        }
-      }
-#pragma unroll 2
-      for (int r = 0; r < CW_XR; ++r) {
-        const int row = h0 - 1 + r;
-        const bool row_ok = row >= 0 && row < H;
-        float v[3][3];                       // [kw][c]
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            v[d][c] = (row_ok && cok[d]) ? __ldg(in + off[d] + c * cstride + (size_t)row * Wv) : 0.f;
-        uint4 lo, hi;
-        __nv_bfloat162 t;
-        t = __floats2bfloat162_rn(v[0][0], v[0][1]); lo.x = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2bfloat162_rn(v[0][2], v[1][0]); lo.y = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2bfloat162_rn(v[1][1], v[1][2]); lo.z = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2bfloat162_rn(v[2][0], v[2][1]); lo.w = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2bfloat162_rn(v[2][2], 1.0f);    hi.x = *reinterpret_cast<uint32_t*>(&t);
-        hi.y = hi.z = hi.w = 0u;
-        *reinterpret_cast<uint4*>(xs + (r * 2) * PSD + tid * 16) = lo;
-        *reinterpret_cast<uint4*>(xs + (r * 2 + 1) * PSD + tid * 16) = hi;
-      }
-      umma::fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core's reads
-      umma::mbar_arrive(&bars->full[stage]);
-    }
-  } else {
-    // =========================== MMA issuer (warp 4) ===============================================
-    constexpr uint32_t idesc = umma::make_idesc_bf16(128, CW_RB * 32, true, true);
-    constexpr uint32_t ab_hi = umma::desc_hi(PSD);       // SBO: stride between 8-channel chunks (planes)
-    uint32_t n = 0, fresh = 1;
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const uint32_t stage = n & 1;
-      umma::mbar_wait(&bars->full[stage], (n >> 1) & 1);
-      umma::fence_proxy_async_smem();
-      umma::tc_fence_after_sync();
-      const uint32_t xs = umma::smem_u32(smem + stage * CW_STAGE);
-      const uint32_t x_lo = umma::desc_lo(xs, 128), d_lo = umma::desc_lo(xs + CW_X_BYTES, 128);
-      if (umma::elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < TILE_M / 16; ++ks)
-          umma::mma_bf16_lohi(tmem, x_lo + ks * 16, ab_hi, d_lo + ks * 16, ab_hi, idesc, (fresh && ks == 0) ? 0u : 1u);
-        umma::mma_commit(&bars->empty[stage]);
-      }
-      fresh = 0;
-      __syncwarp();
-    }
-    if (umma::elect_one()) umma::mma_commit(&bars->done);
-  }
-  // =========================== epilogue: TMEM -> per-CTA partials (warps 0..3) ======================
-  __syncwarp();
-  if (warp < 4) {
-    mbar_wait_relaxed(&bars->done, 0);
-    umma::tc_fence_after_sync();
-    const int r = 2 * warp + (lane >> 4), j = lane & 15;     // TMEM lane = r*16 + j
-    float* out = partial + (size_t)blockIdx.x * CW_PARTIAL;
-#pragma unroll 1
-    for (int q = 0; q < CW_RB; ++q) {
-      uint32_t v[32];
-      umma::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + q * 32, v);
-      umma::tmem_ld_wait();
-      const int kh = r - q;
-      if (kh >= 0 && kh <= 2 && j < 10) {
-        float4* dst = reinterpret_cast<float4*>(out + ((q * 3 + kh) * 10 + j) * C);
-#pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4)
-          dst[g4] = make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]),
-                                __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
-      }
-    }
-  }
-  umma::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 4) umma::tmem_dealloc(tmem, 256);
-}
-
-// block (kh, j): sums partial[cta][q][kh][j][co] over the nslots = CTAs x 6 (cta, q) slots in a fixed order
-__global__ void __launch_bounds__(256) c1_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nslots,
-                                                                 float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float red[8][C];
-  const int kh = blockIdx.x / 10, j = blockIdx.x % 10;
-  const int co = threadIdx.x & 31, g = threadIdx.x >> 5;
-  float s = 0.f;
-  for (int slot = g; slot < nslots; slot += 8) s += partial[(((size_t)slot * 3 + kh) * 10 + j) * C + co];
-  red[g][co] = s;
-  __syncthreads();
-  if (g == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][co];
-    if (j < 9) dw[((co * 3 + j % 3) * 3 + kh) * 3 + j / 3] = t;
-    else if (kh == 1) db[co] = t;
-  }
-}
-
 }  // namespace
 
 #ifdef DD_S1_PROF
@@ -1230,35 +1052,21 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
   return fail(DD_ERR_UNSUPPORTED, "conv_tc: mode %d stride %d", mode, stride);
 }
 
-int conv_c1_fwd_tc(const float* in, int in_is_views, const float* w, const float* bias, void* out, int B, int H, int Wm,
+// in_flags: bit 0 = six views [B,6,3,H,W] (stitch folded in), else a mosaic [B,3,H,Wm]; bit 1 = raw camera bytes (u8, /255 folded in)
+int conv_c1_fwd_tc(const void* in, int in_flags, const float* w, const float* bias, void* out, int B, int H, int Wm,
                    cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(out) & 31) != 0) return fail(DD_ERR_ALIGNMENT, "conv_c1_tc: out %p is not 32-byte aligned", out);
   const int items = B * ((Wm + TILE_M - 1) / TILE_M) * ((H + ROWS - 1) / ROWS);
   const int grid = items < kSMs ? items : kSMs;
-  auto launch1 = [&](auto k) {
+  auto launch1 = [&](auto k, auto* typed_in) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM);
     if (e != cudaSuccess) return fail((int)e, "conv_c1_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    k<<<grid, C1_THREADS, C1_SMEM, st>>>(in, w, bias, (__nv_bfloat16*)out, B, H, Wm);
+    k<<<grid, C1_THREADS, C1_SMEM, st>>>(typed_in, w, bias, (__nv_bfloat16*)out, B, H, Wm);
     return check_launch("conv_c1_tc");
   };
-  return in_is_views ? launch1(conv_c1_tc_kernel<true>) : launch1(conv_c1_tc_kernel<false>);
-}
-
-int conv_c1_wgrad_tc(const float* in, int in_is_views, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes,
-                     int B, int H, int Wm, cudaStream_t st) {
-  const int items = B * ((Wm + TILE_M - 1) / TILE_M) * ((H + CW_RB - 1) / CW_RB);
-  const int grid = items < kSMs ? items : kSMs;
-  const size_t need = (size_t)grid * CW_PARTIAL * sizeof(float);
-  if (ws_bytes < need) return fail(DD_ERR_WORKSPACE, "tcgen05 c1 wgrad: workspace %zu < %zu", ws_bytes, need);
-  auto launch1 = [&](auto k) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM);
-    if (e != cudaSuccess) return fail((int)e, "conv_c1_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    k<<<grid, WG_THREADS, CW_SMEM, st>>>(in, (const __nv_bfloat16*)dy, (float*)ws, B, H, Wm);
-    return check_launch("conv_c1_wgrad_tc");
-  };
-  if (int err = in_is_views ? launch1(conv_c1_wgrad_tc_kernel<true>) : launch1(conv_c1_wgrad_tc_kernel<false>)) return err;
-  c1_wgrad_tc_reduce_kernel<<<30, 256, 0, st>>>((const float*)ws, grid * CW_RB, dw, db);
-  return check_launch("c1_wgrad_tc_reduce");
+  const bool views = in_flags & 1, u8 = in_flags & 2;
+  if (u8) return views ? launch1(conv_c1_tc_kernel<true, uint8_t>, (const uint8_t*)in) : launch1(conv_c1_tc_kernel<false, uint8_t>, (const uint8_t*)in);
+  return views ? launch1(conv_c1_tc_kernel<true, float>, (const float*)in) : launch1(conv_c1_tc_kernel<false, float>, (const float*)in);
 }
 
 }  // namespace dd

@@ -274,21 +274,260 @@ __global__ void wgrad_ring_reduce_kernel(const float* __restrict__ partial, int 
   }
 }
 
-// NHWC bf16 [B][H][W][32] as a 4-D tensor (c, w, h, b): box = 32 channels x box_w SOURCE pixels of one row, taking every
-// estride-th pixel, 64-byte swizzle (inner extent = one 64-byte pixel).  Out-of-range -> zeros.
-int map_nhwc_sw64(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint32_t box_w, uint32_t estride) {
-  dd::EncodeTiledFn enc = dd::tma_encoder();
-  if (!enc) return -1;
-  static thread_local bool ctx_bound = false;
-  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
-  const cuuint64_t dims[4] = {32, W, H, B};
-  const cuuint64_t strides[3] = {64, W * 64, H * W * 64};
-  const cuuint32_t box[4] = {32, box_w, 1, 1};
-  const cuuint32_t estr[4] = {1, estride, 1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)r;
+// ================================================================================================
+// Weight gradient of the first conv (3 -> 32, components.py:19,41), stitch (and the ToTensor /255 of raw camera
+// bytes) folded into the loads:
+//   dW[co][c][kh][kw] = sum_{b,h,w} in[b,c,h+kh-1,w+kw-1] * dy[b,h,w,co],   db[co] = sum dy[b,h,w,co]
+// Same march as above (pixels = K, a CTA walks down a 128-pixel column strip), with
+//   B = 4 dy rows per step, whole-pixel TMA boxes, 64-byte swizzle (N = 4 x 32 co = 128);
+//   A = 8 x rows of "tap-packed" pixels built by four converter warps from the fp32 / u8 image: 16 channels per pixel,
+//       channel j = kw*3 + c (j < 9) = in[c][p + kw - 1], j = 9 is 1.0 (-> the bias gradient rides along), rest 0 --
+//       the three horizontal taps sit in the M dimension instead of costing three MMAs.  SWIZZLE_NONE MN-major:
+//       two [pixel][8 ch] planes per row.  Each image row is read and converted ONCE per strip (thread = pixel column;
+//       the left / right neighbours come from the adjacent lanes by shuffle), round 1 re-read 8 rows per 6.
+// Block (r, q) of D = tap kh = r - q.  One stage = {4 x rows, 4 dy rows}; a step reads the x rows of two stages.
+// Warps 0-3 converters (+ the final epilogue), 4 = MMA issuer, 5 = TMA producer for dy.
+// ================================================================================================
+constexpr int C1_RB = 4;                       // dy rows (and new x rows) per stage
+constexpr int C1_NS = 4;                       // stages
+constexpr int C1_PL = KP * 16;                 // one [128 px][8 ch] plane: 2048 B
+constexpr int C1_XROW = 2 * C1_PL;             // x ring slot = one row = two planes
+constexpr int C1_XBYTES = (C1_RB * C1_NS + C1_RB) * C1_XROW;     // + mirror of stage slot 0
+constexpr int C1_DBYTES = C1_NS * C1_RB * DROW;
+constexpr int C1_SMEM = C1_XBYTES + C1_DBYTES + 256;
+constexpr int C1_HSEG = 64;
+constexpr int C1_PARTIAL = C1_RB * 3 * 10 * C;  // floats per CTA: [q][kh][j][co]
+constexpr int C1_THREADS = 192;
+static_assert(C1_SMEM <= 227 * 1024, "shared memory");
+
+template <typename TIN> __device__ __forceinline__ float c1_ld(const TIN* p);
+template <> __device__ __forceinline__ float c1_ld<float>(const float* p) { return __ldg(p); }
+// torchvision ToTensor (data_helper.py:109-114): byte -> float32, divided by 255 (IEEE division: bit-identical)
+template <> __device__ __forceinline__ float c1_ld<uint8_t>(const uint8_t* p) { return __fdiv_rn((float)__ldg(p), 255.0f); }
+
+template <bool IS_VIEWS, typename TIN>
+__global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_wgrad_ring_kernel(const TIN* __restrict__ in,
+                                                                           const __grid_constant__ CUtensorMap map_dy,
+                                                                           float* __restrict__ partial, int B, int H, int Wm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_x = smem;
+  uint8_t* s_d = smem + C1_XBYTES;
+  RingBars* bars = reinterpret_cast<RingBars*>(smem + C1_XBYTES + C1_DBYTES);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wtiles = (Wm + KP - 1) / KP;
+  const int hsegs = (H + C1_HSEG - 1) / C1_HSEG;
+  const int items = B * wtiles * hsegs;
+
+  if (tid == 0) {
+    // per stage: 128 converter arrivals (planes written and fenced) + the producer's expect_tx arrival (dy rows)
+    for (int i = 0; i < C1_NS; ++i) { umma::mbar_init(&bars->full[i], 129); umma::mbar_init(&bars->empty[i], 1); }
+    umma::mbar_init(&bars->done, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == 4) umma::tmem_alloc(&bars->tmem_base, 128);
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
+
+  if (warp < 4) {
+    // =========================== converters: thread = pixel column of the strip ====================
+    // The image loads of stage g + 1 are issued BEFORE stage g is packed and stored (register double buffer): a stage's
+    // global-load latency is hidden behind the previous stage's work instead of sitting on the ring's critical path.
+    const int Wv = IS_VIEWS ? Wm / 6 : Wm;
+    const size_t cstride = (size_t)H * Wv;
+    const bool has_edge = lane == 0 || lane == 31;
+    struct Cur { int it, i, P, xr0; size_t coff, eoff; bool cok, eok, valid; };
+    auto open_item = [&](Cur& c) {
+      c.valid = c.it < items;
+      if (!c.valid) return;
+      const int wt = c.it % wtiles, hs = (c.it / wtiles) % hsegs, b = c.it / (wtiles * hsegs);
+      const int h0 = hs * C1_HSEG, w0 = wt * KP;
+      c.P = (min(C1_HSEG, H - h0) + C1_RB - 1) / C1_RB;
+      c.i = 0;
+      c.xr0 = h0 - 1;
+      // this thread's column, and for the warp's edge lanes the column just outside the warp (lane 0: left, 31: right)
+      const int col = w0 + tid;
+      const int ecol = lane == 0 ? col - 1 : col + 1;
+      auto col_off = [&](int cc, bool& ok) -> size_t {
+        ok = cc >= 0 && cc < Wm;
+        const int c2 = ok ? cc : 0;
+        if (IS_VIEWS) {
+          const int j = c2 / Wv, w = c2 - j * Wv;
+          return (((size_t)b * 6 + dd::view_of_slot(j)) * 3) * cstride + w;
+        }
+        return ((size_t)b * 3) * cstride + c2;
+      };
+      c.coff = col_off(col, c.cok);
+      c.eoff = col_off(ecol, c.eok);
+    };
+    auto advance = [&](Cur& c) {
+      if (c.i < c.P) { ++c.i; c.xr0 += C1_RB; return; }
+      c.it += gridDim.x;
+      open_item(c);
+    };
+    auto load_rows = [&](const Cur& c, float (&v)[C1_RB][3], float (&e)[C1_RB][3]) {
+#pragma unroll
+      for (int r = 0; r < C1_RB; ++r) {
+        const int row = c.xr0 + r;
+        const bool row_ok = row >= 0 && row < H;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          v[r][ch] = (row_ok && c.cok) ? c1_ld<TIN>(in + c.coff + ch * cstride + (size_t)row * Wv) : 0.f;
+          e[r][ch] = (has_edge && row_ok && c.eok) ? c1_ld<TIN>(in + c.eoff + ch * cstride + (size_t)row * Wv) : 0.f;
+        }
+      }
+    };
+    Cur cur;
+    cur.it = blockIdx.x;
+    open_item(cur);
+    float v[C1_RB][3], e[C1_RB][3], vn[C1_RB][3], en[C1_RB][3];
+    if (cur.valid) load_rows(cur, v, e);
+    uint32_t g = 0;
+    while (cur.valid) {
+      Cur nxt = cur;
+      advance(nxt);
+      if (nxt.valid) load_rows(nxt, vn, en);
+      const uint32_t s = g % C1_NS;
+      umma::mbar_wait(&bars->empty[s], ((g / C1_NS) & 1) ^ 1);
+#pragma unroll
+      for (int r = 0; r < C1_RB; ++r) {
+        float lf[3], rt[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          lf[c] = __shfl_up_sync(0xffffffffu, v[r][c], 1);
+          rt[c] = __shfl_down_sync(0xffffffffu, v[r][c], 1);
+          if (lane == 0) lf[c] = e[r][c];
+          if (lane == 31) rt[c] = e[r][c];
+        }
+        uint4 lo, hi;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(lf[0], lf[1]);           lo.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(lf[2], v[r][0]);         lo.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[r][1], v[r][2]);       lo.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(rt[0], rt[1]);           lo.w = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(rt[2], 1.0f);            hi.x = *reinterpret_cast<uint32_t*>(&t);
+        hi.y = hi.z = hi.w = 0u;
+        uint8_t* dst = s_x + (size_t)(C1_RB * s + r) * C1_XROW + tid * 16;
+        *reinterpret_cast<uint4*>(dst) = lo;
+        *reinterpret_cast<uint4*>(dst + C1_PL) = hi;
+        if (s == 0) {                                    // mirror of stage slot 0 behind the ring's last slot
+          uint8_t* dm = s_x + (size_t)(C1_RB * C1_NS + r) * C1_XROW + tid * 16;
+          *reinterpret_cast<uint4*>(dm) = lo;
+          *reinterpret_cast<uint4*>(dm + C1_PL) = hi;
+        }
+      }
+      umma::fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core's reads
+      umma::mbar_arrive(&bars->full[s]);
+      ++g;
+#pragma unroll
+      for (int r = 0; r < C1_RB; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { v[r][c] = vn[r][c]; e[r][c] = en[r][c]; }
+      cur = nxt;
+    }
+  } else if (warp == 5) {
+    // =========================== producer: dy rows by TMA (one thread) ================================
+    if (lane == 0) {
+      umma::tma_prefetch_desc(&map_dy);
+      uint32_t g = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+        const int h0 = hs * C1_HSEG, w0 = wt * KP;
+        const int rows = min(C1_HSEG, H - h0);
+        const int P = (rows + C1_RB - 1) / C1_RB;
+        for (int i = 0; i <= P; ++i, ++g) {
+          const uint32_t s = g % C1_NS;
+          umma::mbar_wait(&bars->empty[s], ((g / C1_NS) & 1) ^ 1);
+          if (i < P) {
+            umma::mbar_expect_tx(&bars->full[s], C1_RB * DROW);
+#pragma unroll
+            for (int q = 0; q < C1_RB; ++q)
+              umma::tma_load_4d(umma::smem_u32(s_d) + (s * C1_RB + q) * DROW, &map_dy, 0, w0, h0 + C1_RB * i + q, b, &bars->full[s]);
+          } else {
+            umma::mbar_arrive(&bars->full[s]);             // the item's last stage carries x rows only
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== MMA issuer (warp 4) ===================================================
+    constexpr uint32_t idesc = umma::make_idesc_bf16(128, C1_RB * 32, true, true);
+    constexpr uint32_t a_hi = umma::desc_hi(C1_PL);                                   // A: SBO = next 8-channel chunk (plane), no swizzle
+    constexpr uint32_t b_hi = ((512u >> 4) & 0x3FFF) | (1u << 14) | (4u << 29);       // B: SBO = 512 B, SWIZZLE_64B
+    const uint32_t x_lo0 = umma::desc_lo(umma::smem_u32(s_x), 128);                   // A: LBO = next 8-pixel group
+    const uint32_t d_lo0 = umma::desc_lo(umma::smem_u32(s_d), DROW);                  // B: LBO = next dy row
+    uint32_t g = 0, waited = 0, fresh = 1;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int hs = (it / wtiles) % hsegs;
+      const int rows = min(C1_HSEG, H - hs * C1_HSEG);
+      const int P = (rows + C1_RB - 1) / C1_RB;
+      for (int j = 0; j < P; ++j, ++g) {
+        for (; waited < g + 2; ++waited) umma::mbar_wait(&bars->full[waited % C1_NS], (waited / C1_NS) & 1);
+        umma::tc_fence_after_sync();
+        const uint32_t s = g % C1_NS;
+        const uint32_t a0 = x_lo0 + ((C1_RB * s * C1_XROW) >> 4);
+        const uint32_t b0 = d_lo0 + ((s * C1_RB * DROW) >> 4);
+        if (umma::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < KP / 16; ++ks)
+            umma::mma_bf16_lohi(tmem, a0 + ks * 16, a_hi, b0 + ((ks * 1024) >> 4), b_hi, idesc, (fresh && ks == 0) ? 0u : 1u);
+          umma::mma_commit(&bars->empty[s]);
+          if (j == P - 1) umma::mma_commit(&bars->empty[(g + 1) % C1_NS]);
+        }
+        fresh = 0;
+        __syncwarp();
+      }
+      ++g;
+    }
+    if (umma::elect_one()) umma::mma_commit(&bars->done);
+    __syncwarp();
+  }
+  // =========================== epilogue: TMEM -> per-CTA partials (warps 0..3) ==========================
+  __syncwarp();
+  if (warp < 4) {
+    mbar_wait_backoff(&bars->done, 0);
+    umma::tc_fence_after_sync();
+    const int r = 2 * warp + (lane >> 4), j = lane & 15;     // TMEM lane = r*16 + j
+    float* out = partial + (size_t)blockIdx.x * C1_PARTIAL;
+#pragma unroll 1
+    for (int q = 0; q < C1_RB; ++q) {
+      uint32_t v[32];
+      umma::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + q * 32, v);
+      umma::tmem_ld_wait();
+      const int kh = r - q;
+      if (kh >= 0 && kh <= 2 && j < 10) {
+        float4* dst = reinterpret_cast<float4*>(out + ((q * 3 + kh) * 10 + j) * C);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4)
+          dst[g4] = make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]), __uint_as_float(v[4 * g4 + 2]),
+                                __uint_as_float(v[4 * g4 + 3]));
+      }
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) umma::tmem_dealloc(tmem, 128);
+}
+
+// block (kh, j): sums partial[slot][kh][j][co] over the nslots = CTAs x 4 (cta, q) slots in a fixed order
+__global__ void __launch_bounds__(256) c1_wgrad_ring_reduce_kernel(const float* __restrict__ partial, int nslots,
+                                                                   float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[8][C];
+  const int kh = blockIdx.x / 10, j = blockIdx.x % 10;
+  const int co = threadIdx.x & 31, g = threadIdx.x >> 5;
+  float s = 0.f;
+  for (int slot = g; slot < nslots; slot += 8) s += partial[(((size_t)slot * 3 + kh) * 10 + j) * C + co];
+  red[g][co] = s;
+  __syncthreads();
+  if (g == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][co];
+    if (j < 9) dw[((co * 3 + j % 3) * 3 + kh) * 3 + j / 3] = t;
+    else if (kh == 1) db[co] = t;
+  }
 }
 
 template <int STRIDE>
@@ -310,13 +549,13 @@ int wgrad_ring_launch(const void* x, const void* dy, float* dw, float* db, void*
   CUtensorMap mx = {}, mx1 = {}, mdy = {};
   int r;
   if (STRIDE == 1) {
-    r = map_nhwc_sw64(&mx, x, (uint64_t)B, (uint64_t)H, (uint64_t)W, 130, 1);
+    r = dd::tma_map_nhwc_sw64(&mx, x, (uint64_t)B, (uint64_t)H, (uint64_t)W, 130, 1);
   } else {
-    r = map_nhwc_sw64(&mx, x, (uint64_t)B, (uint64_t)H, (uint64_t)W, 255, 2);          // 255 source pixels -> 128 loaded
-    if (!r) r = map_nhwc_sw64(&mx1, x, (uint64_t)B, (uint64_t)H, (uint64_t)W, 1, 1);
+    r = dd::tma_map_nhwc_sw64(&mx, x, (uint64_t)B, (uint64_t)H, (uint64_t)W, 255, 2);          // 255 source pixels -> 128 loaded
+    if (!r) r = dd::tma_map_nhwc_sw64(&mx1, x, (uint64_t)B, (uint64_t)H, (uint64_t)W, 1, 1);
   }
   if (r) return dd::fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: cuTensorMapEncodeTiled(x) -> %d", r);
-  if ((r = map_nhwc_sw64(&mdy, dy, (uint64_t)B, (uint64_t)Ho, (uint64_t)Wo, KP, 1)))
+  if ((r = dd::tma_map_nhwc_sw64(&mdy, dy, (uint64_t)B, (uint64_t)Ho, (uint64_t)Wo, KP, 1)))
     return dd::fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: cuTensorMapEncodeTiled(dy) -> %d", r);
   k<<<grid, WGT_THREADS, G::SMEM, st>>>(mx, mx1, mdy, partial, dbp, B, Ho, Wo);
   if (int err = dd::check_launch("conv3x3_c32_wgrad_ring")) return err;
@@ -333,6 +572,35 @@ int conv3x3_c32_wgrad_tc(const void* x, const void* dy, float* dw, float* db, vo
   if (stride == 1) return wgrad_ring_launch<1>(x, dy, dw, db, ws, ws_bytes, B, H, W, st);
   if (stride == 2) return wgrad_ring_launch<2>(x, dy, dw, db, ws, ws_bytes, B, H, W, st);
   return fail(DD_ERR_UNSUPPORTED, "tcgen05 wgrad: stride %d", stride);
+}
+
+
+// in_flags: bit 0 = `in` holds the six views [B,6,3,H,W] (stitch folded in), else a mosaic [B,3,H,Wm]; bit 1 = raw bytes (u8)
+int conv_c1_wgrad_tc(const void* in, int in_flags, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes, int B,
+                     int H, int Wm, cudaStream_t st) {
+  const int items = B * ((Wm + KP - 1) / KP) * ((H + C1_HSEG - 1) / C1_HSEG);
+  const int grid = items < kSMs ? items : kSMs;
+  const size_t need = (size_t)grid * C1_PARTIAL * sizeof(float);
+  if (ws_bytes < need) return fail(DD_ERR_WORKSPACE, "tcgen05 c1 wgrad: workspace %zu < %zu", ws_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(dy) & 15) != 0) return fail(DD_ERR_ALIGNMENT, "tcgen05 c1 wgrad: dy is not 16-byte aligned");
+  CUtensorMap mdy;
+  if (int r = dd::tma_map_nhwc_sw64(&mdy, dy, (uint64_t)B, (uint64_t)H, (uint64_t)Wm, KP, 1))
+    return fail(DD_ERR_UNSUPPORTED, "tcgen05 c1 wgrad: cuTensorMapEncodeTiled(dy) -> %d", r);
+  auto launch1 = [&](auto k, auto* typed_in) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "conv_c1_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    k<<<grid, C1_THREADS, C1_SMEM, st>>>(typed_in, mdy, (float*)ws, B, H, Wm);
+    return check_launch("conv_c1_wgrad_ring");
+  };
+  int err;
+  const bool views = in_flags & 1, u8 = in_flags & 2;
+  if (u8) err = views ? launch1(conv_c1_wgrad_ring_kernel<true, uint8_t>, (const uint8_t*)in)
+                      : launch1(conv_c1_wgrad_ring_kernel<false, uint8_t>, (const uint8_t*)in);
+  else err = views ? launch1(conv_c1_wgrad_ring_kernel<true, float>, (const float*)in)
+                   : launch1(conv_c1_wgrad_ring_kernel<false, float>, (const float*)in);
+  if (err) return err;
+  c1_wgrad_ring_reduce_kernel<<<30, 256, 0, st>>>((const float*)ws, grid * C1_RB, dw, db);
+  return check_launch("c1_wgrad_ring_reduce");
 }
 
 }  // namespace dd

@@ -65,6 +65,28 @@ inline int tma_map_nhwc_c8(CUtensorMap* map, const void* base, uint64_t B, uint6
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// NHWC bf16 activation [B][H][W][32] as a 4-D tensor (c, w, h, b) with a box of WHOLE pixels: 32 channels x box_w SOURCE
+// pixels of one row, taking every estride-th pixel (box_w <= 256; estride 2 -> ceil(box_w / 2) pixels land), 64-byte
+// swizzle (inner extent = one 64-byte pixel).  The tile that lands is at once the K-major SWIZZLE_64B operand of a forward
+// conv (rows = pixels, K = channels) and the MN-major one of a weight gradient (K = pixels); a tap is a shift of the
+// operand's start address by whole pixels (tools/tma_layout_probe.cu, tools/tma_sw64_mn_probe.cu).  Full 32-byte
+// sectors from L2 and one request per row, against half sectors and four requests with tma_map_nhwc_c8.
+inline int tma_map_nhwc_sw64(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint32_t box_w,
+                             uint32_t estride = 1) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc) return -1;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  const cuuint64_t dims[4] = {32, W, H, B};
+  const cuuint64_t strides[3] = {64, W * 64, H * W * 64};
+  const cuuint32_t box[4] = {32, box_w, 1, 1};
+  const cuuint32_t estr[4] = {1, estride, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 // last failing encode, for error texts
 inline int tma_map_2d_checked(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
                               uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows, bool atom32, char* msg, size_t msg_len) {

@@ -215,6 +215,13 @@ namespace umma {
 __device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);   // version 1, layout_type 2 = SWIZZLE_128B (bits 61-63)
 }
+// SWIZZLE_64B (layout_type 4): what a whole-pixel TMA box of a 32-channel bf16 NHWC row produces (64-byte rows, 8-row atoms of
+// 512 B).  K-major: rows = M/N index, SBO = stride between 8-row groups, K advances inside the row (+32 B per K = 16).
+// MN-major: rows = K index, LBO = stride between 32-element MN blocks, SBO = stride between 8-row K groups.
+// The swizzle follows the absolute shared-memory address: a start address shifted by whole rows works with base_offset 0.
+__host__ __device__ constexpr uint32_t desc_hi_sw64(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (4u << 29);
+}
 // SWIZZLE_128B_BASE32B (layout_type 1): the only layout for MN-major tf32 operands; 4-row K atoms
 // (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); SBO = stride between groups of 4 K rows
 __device__ __forceinline__ uint32_t desc_hi_sw128_base32(uint32_t sbo_bytes) {

@@ -60,13 +60,16 @@ int dd_stitch_mask_f32(const float* views, float* x, float* y, int B, int H, int
 int dd_stitch_u8(const uint8_t* views, float* mosaic, int B, int H, int W, void* stream);
 
 /* ---- A3: encoder convs (components.py:19-21,41-43) ------------------------------------------
- * c1: 3->32, 3x3, pad 1, + bias + ReLU.  `in` is either the views [B,6,3,H,W] (in_is_views=1:
- * the stitch is folded into the loads, Wm = 6W) or a mosaic / any NCHW image [B,3,H,Wm]
- * (in_is_views=0).  out: NHWC [B,H,Wm,32] of out_dtype. */
-int dd_conv_c1_fwd(const float* in, int in_is_views, const float* w_oihw, const float* bias,
+ * c1: 3->32, 3x3, pad 1, + bias + ReLU.  `in` is either the views [B,6,3,H,W] (in_flags &
+ * DD_IN_VIEWS: the stitch is folded into the loads, Wm = 6W) or a mosaic / any NCHW image
+ * [B,3,H,Wm]; fp32 in [0,1], or -- with DD_IN_U8, bf16 tensor-core path only -- the raw camera
+ * bytes, with torchvision ToTensor's /255 (data_helper.py:109-114, roadmap_bce_v2.py:171) folded
+ * into the loads, bit-identical to x.float()/255.  out: NHWC [B,H,Wm,32] of out_dtype. */
+enum { DD_IN_VIEWS = 1, DD_IN_U8 = 2 };
+int dd_conv_c1_fwd(const void* in, int in_flags, const float* w_oihw, const float* bias,
                    void* out, int out_dtype, int B, int H, int Wm, int impl, void* stream);
 /* dW [32,3,3,3], db [32] from dy = dL/d(out) ALREADY masked by out>0.  workspace: see below. */
-int dd_conv_c1_wgrad(const float* in, int in_is_views, const void* dy, int dtype, float* dw,
+int dd_conv_c1_wgrad(const void* in, int in_flags, const void* dy, int dtype, float* dw,
                      float* db, void* workspace, size_t ws_bytes, int B, int H, int Wm, int impl,
                      void* stream);
 

@@ -241,6 +241,49 @@ def test_conv_c1_fwd_and_wgrad(dd, dtype, tol, B, H, W, impl):
         assert rel_max_err(db, bq.grad) < tol
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 16, 20), (1, 33, 7), (2, 70, 50), (2, 256, 306)])
+def test_conv_c1_tcgen05_raw_bytes_and_full_size(dd, B, H, W):
+    """The u8 front-end (data_helper.py:109-114 ToTensor folded into c1's loads, DD_IN_U8): forward and weight gradient
+    from raw camera bytes are BIT-IDENTICAL to the same kernels fed ``bytes.float() / 255`` -- and the fp32 forms agree
+    with autograd, here also at the full 256 x 1836 mosaic (several row segments and column strips per CTA)."""
+    from driving_dirty_b200._lib import call, dtype_code, load, stream_ptr
+    g = torch.Generator().manual_seed(33)
+    raw = torch.randint(0, 256, (B, 6, 3, H, W), dtype=torch.uint8, generator=g)
+    views = raw.float() / 255                               # what ToTensor hands the reference
+    _, w, b = _conv_inputs(1, 4, 4, seed=32, cin=3)
+    mosaic = so.stitch(views)
+    wq, bq = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = F.relu(F.conv2d(mosaic, wq, bq, padding=1))
+    dtype, Wm, st = torch.bfloat16, 6 * W, stream_ptr()
+    code = dtype_code(dtype)
+    wc, bc = w.cuda(), b.cuda()
+    outs = []
+    for flags, src in ((1, views.cuda()), (3, raw.cuda()), (2, so.stitch(raw).cuda())):
+        out = torch.empty(B, H, Wm, 32, dtype=dtype, device="cuda")
+        call("dd_conv_c1_fwd", src.data_ptr(), flags, wc.data_ptr(), bc.data_ptr(), out.data_ptr(), code, B, H, Wm, 2, st)
+        outs.append(out)
+    assert rel_max_err(to_nchw(outs[0]), y) < BF16_TOL
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    dy = q(torch.randn(y.shape, generator=g), dtype) * (y.detach() > 0)
+    y.backward(dy)
+    n = int(load().dd_conv_wgrad_workspace_bytes())
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dyin = nhwc(dy, dtype)
+    res = []
+    for flags, src in ((1, views.cuda()), (3, raw.cuda()), (2, so.stitch(raw).cuda()), (3, raw.cuda())):
+        dw, db = torch.empty(32, 3, 3, 3, device="cuda"), torch.empty(32, device="cuda")
+        call("dd_conv_c1_wgrad", src.data_ptr(), flags, dyin.data_ptr(), code, dw.data_ptr(), db.data_ptr(),
+             ws.data_ptr(), n, B, H, Wm, 2, st)
+        res.append((dw.clone(), db.clone()))
+    assert rel_max_err(res[0][0], wq.grad) < BF16_TOL and rel_max_err(res[0][1], bq.grad) < 2e-4
+    for dw, db in res[1:]:
+        assert torch.equal(dw, res[0][0]) and torch.equal(db, res[0][1])      # same bits from bytes, run to run
+    # the fp32 parity path refuses raw bytes instead of misreading them
+    with pytest.raises(RuntimeError):
+        call("dd_conv_c1_fwd", raw.cuda().data_ptr(), 3, wc.data_ptr(), bc.data_ptr(),
+             torch.empty(B, H, Wm, 32, device="cuda").data_ptr(), dtype_code(torch.float32), B, H, Wm, 0, st)
+
+
 # ------------------------------------------------------------------------------- pool --------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W", [(2, 8, 60), (2, 5, 42), (1, 3, 7), (1, 128, 918)])
