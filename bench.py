@@ -336,7 +336,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from driving_dirty_b200 import _lib
     from driving_dirty_b200.optim import FusedAdam
-    from driving_dirty_b200.synthetic import scene_batch
+    from driving_dirty_b200.synthetic import scene_batch_bytes
 
     B = args.batch
     model = build_model(args.dtype, dev)
@@ -345,10 +345,13 @@ def run_ours(args):
     # ONE kernel over NVLink peer memory (optim.FusedAdam / csrc/adam.cu), the small tensors by one flat NCCL all-reduce
     opt = FusedAdam(params, lr=1e-3, overlap_backward=True)
 
-    # synthetic scenes: a different batch per rank, pinned on the host, one resident copy in HBM
-    views_h, road_h = scene_batch(B, VIEW_H, VIEW_W, seed=20200506 + rank)
+    # synthetic scenes: a different batch per rank, pinned on the host, one resident copy in HBM.  The views are raw
+    # camera bytes (uint8, what the JPEG decoder yields): ToTensor's /255 (data_helper.py:109-114) is folded into the first
+    # conv's loads, bit-identical to feeding bytes.float()/255 (tests/test_modules_gpu.py::test_raw_byte_front_end_...).
+    views_h, road_h = scene_batch_bytes(B, VIEW_H, VIEW_W, seed=20200506 + rank)
     views_h, road_h = views_h.pin_memory(), road_h.pin_memory()
     views_d, road_d = views_h.to(dev, non_blocking=True), road_h.to(dev, non_blocking=True)
+    views_f32_h = (views_h.float() / 255).pin_memory()      # what the reference's dataloader hands over (for e2e_f32_views)
 
     def step(views, road):
         opt.zero_grad(set_to_none=True)
@@ -388,35 +391,41 @@ def run_ours(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     loss_h = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            bufs[i][0].copy_(views_h, non_blocking=True)
-            bufs[i][1].copy_(road_h, non_blocking=True)
-            ready[i].record(copy_stream)
+    def e2e_time(src_views, bufs):
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                bufs[i][0].copy_(src_views, non_blocking=True)
+                bufs[i][1].copy_(road_h, non_blocking=True)
+                ready[i].record(copy_stream)
 
-    def e2e_loop(k):
-        prefetch(0)
-        for i in range(k):
-            cur = i & 1
-            torch.cuda.current_stream().wait_event(ready[cur])
-            if i + 1 < k:
-                copy_stream.wait_stream(torch.cuda.current_stream())   # buffer (i+1)&1 was consumed by step i-1
-                prefetch((i + 1) & 1)
-            l = step(bufs[cur][0], bufs[cur][1])
-            loss_h.copy_(l.detach(), non_blocking=False)               # D2H read of the step's result
+        def e2e_loop(k):
+            prefetch(0)
+            for i in range(k):
+                cur = i & 1
+                torch.cuda.current_stream().wait_event(ready[cur])
+                if i + 1 < k:
+                    copy_stream.wait_stream(torch.cuda.current_stream())   # buffer (i+1)&1 was consumed by step i-1
+                    prefetch((i + 1) & 1)
+                l = step(bufs[cur][0], bufs[cur][1])
+                loss_h.copy_(l.detach(), non_blocking=False)               # D2H read of the step's result
 
-    e2e_loop(2)
-    barrier()
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    barrier()
-    sec_e2e = e0.elapsed_time(e1) * 1e-3
+        e2e_loop(2)
+        barrier()
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) * 1e-3
 
-    t = torch.tensor([sec, sec_e2e], device=dev, dtype=torch.float64)
+    sec_e2e = e2e_time(views_h, bufs)
+    bufs32 = [(torch.empty(views_f32_h.shape, device=dev), torch.empty_like(road_d)) for _ in range(2)]
+    sec_e2e_f32 = e2e_time(views_f32_h, bufs32)
+    del bufs32
+
+    t = torch.tensor([sec, sec_e2e, sec_e2e_f32], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sec, sec_e2e = float(t[0]), float(t[1])
+    sec, sec_e2e, sec_e2e_f32 = float(t[0]), float(t[1]), float(t[2])
     verify = verify_data_parallel_step(model, opt, step, views_d, road_d, world) if world > 1 else None
     if verify is not None and not verify["ok"]:
         raise SystemExit(f"bench.py: the data-parallel step failed its self-check: {json.dumps(verify)}")
@@ -440,12 +449,16 @@ def run_ours(args):
             "warmup": max(args.warmup, 5), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"RoadMapBCE train step (BASELINE config 2), {B} scenes/GPU/step, views 6x3x{VIEW_H}x{VIEW_W}, "
-                                   f"hidden {HIDDEN} latent {LATENT}, map {MAP}x{MAP}, encoder unfrozen, Adam (dd_adam_step" + (", sharded over NVLink peer memory" + (" + multicast" if opt.uses_multicast else "") if world > 1 else "") + ")",
+                                   f"hidden {HIDDEN} latent {LATENT}, map {MAP}x{MAP}, views as raw camera bytes (uint8; /255 folded into conv 1), encoder unfrozen, Adam (dd_adam_step" + (", sharded over NVLink peer memory" + (" + multicast" if opt.uses_multicast else "") if world > 1 else "") + ")",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "inputs (180 MB views/step) and activations (GBs) exceed the 126 MB L2; no explicit flush"},
-            "e2e": {"value": total / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": views_h.numel() * 4 + road_h.numel(),
+                       "l2": "activations (2 x 963 MB per layer) and the 1.3 GB of FC weights exceed the 126 MB L2 many times over; no explicit flush"},
+            "e2e": {"value": total / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": views_h.numel() + road_h.numel(),
                     "d2h_bytes_per_step": 4, "ms_per_step": sec_e2e / args.steps * 1e3,
-                    "note": "pinned host views/road maps copied every step on a side stream (double-buffered), loss read back"},
+                    "note": "pinned host views (raw camera bytes, uint8) and bool road maps copied every step on a side stream "
+                            "(double-buffered), loss read back"},
+            "e2e_f32_views": {"value": total / sec_e2e_f32, "unit": UNIT, "h2d_bytes_per_step": views_f32_h.numel() * 4 + road_h.numel(),
+                              "d2h_bytes_per_step": 4, "ms_per_step": sec_e2e_f32 / args.steps * 1e3,
+                              "note": "the same with fp32 host views (what the reference's ToTensor dataloader emits): 4x the H2D bytes"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_rows,
             "cpu_baseline": cpu, "final_loss": final_loss,
         }

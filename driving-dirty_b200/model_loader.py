@@ -25,6 +25,13 @@ def get_transform_task2():
     return torchvision.transforms.ToTensor()
 
 
+def get_transform_bytes():
+    """Front-end for raw camera bytes: the image stays uint8 [3,H,W]; the /255 of ToTensor
+    (data_helper.py:109-114) is folded into the first conv's loads on the device -- 4x fewer host-to-device bytes."""
+    import torchvision
+    return torchvision.transforms.PILToTensor()
+
+
 class ModelLoader:
     team_name = "driving-dirty-b200"
     team_number = 0
@@ -46,12 +53,39 @@ class ModelLoader:
         self.device = torch.device(device)
         self.model = model.to(self.device)
         self.model.eval()
+        self._staging = {}          # (shape, dtype) -> [pinned host buffer, device buffer, copy-done event]
+        self._copy_stream = None
+
+    def stage(self, samples):
+        """Host samples ([B,6,3,H,W] uint8 bytes or fp32) -> device, through a cached PINNED buffer and an asynchronous
+        copy on a side stream (a pageable source would make the copy synchronous and staged by the driver)."""
+        if samples.is_cuda:
+            return samples.to(self.device)
+        key = (tuple(samples.shape), samples.dtype)
+        slot = self._staging.get(key)
+        if slot is None:
+            slot = [torch.empty(samples.shape, dtype=samples.dtype).pin_memory(),
+                    torch.empty(samples.shape, dtype=samples.dtype, device=self.device), torch.cuda.Event()]
+            self._staging[key] = slot
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        host, dev, done = slot
+        done.synchronize()                                   # the previous copy out of the pinned buffer has finished
+        host.copy_(samples)
+        cur = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_stream(cur)                   # the device buffer's previous consumer has finished
+        with torch.cuda.stream(self._copy_stream):
+            dev.copy_(host, non_blocking=True)
+            done.record(self._copy_stream)
+        cur.wait_event(done)
+        return dev
 
     @torch.no_grad()
     def get_binary_road_map(self, samples):
-        """samples: CUDA tensor [B,6,3,256,306] in [0,1] -> CUDA float tensor [B,800,800] of 0./1.,
-        equal to ``sigmoid(logits).round()`` of the reference forward."""
-        logits = self.model._logits(samples.to(self.device))
+        """samples: tensor [B,6,3,256,306], fp32 in [0,1] (the competition's CUDA tensor) or uint8 raw camera bytes, on the
+        device or on the host (then staged through pinned memory) -> CUDA float tensor [B,800,800] of 0./1., equal to
+        ``sigmoid(logits).round()`` of the reference forward (on ``bytes.float() / 255`` for raw bytes)."""
+        logits = self.model._logits(self.stage(samples))
         _, binary = ops.sigmoid_binary(logits)
         return binary.float()
 

@@ -51,7 +51,8 @@ _ws = _Workspaces()
 # --------------------------------------------------------------------------------------------
 def as_view_batch(sample) -> torch.Tensor:
     """tuple/list of B [6,3,H,W] tensors (what collate_fn yields) or a [B,6,3,H,W] tensor ->
-    contiguous [B,6,3,H,W] fp32 CUDA tensor, without a copy when the tuple is ``batch.unbind(0)``."""
+    contiguous [B,6,3,H,W] CUDA tensor, without a copy when the tuple is ``batch.unbind(0)``: fp32 in [0,1] (what
+    ToTensor hands the reference) or uint8 raw camera bytes (the /255 is then folded into the first conv's loads)."""
     if torch.is_tensor(sample):
         x = sample
     else:
@@ -65,14 +66,16 @@ def as_view_batch(sample) -> torch.Tensor:
     _require_cuda(x)
     if x.dim() != 5 or x.shape[1] != 6 or x.shape[2] != 3:
         raise RuntimeError(f"expected views of shape [B,6,3,H,W], got {tuple(x.shape)}")
-    if x.dtype != torch.float32:
+    if x.dtype not in (torch.float32, torch.uint8):
         x = x.float()
     return _c(x)
 
 
 def stitch(views: torch.Tensor) -> torch.Tensor:
-    """wide_stitch_six_images (roadmap_bce_v2.py:53-64): [B,6,3,H,W] -> [B,3,H,6W]."""
+    """wide_stitch_six_images (roadmap_bce_v2.py:53-64): [B,6,3,H,W] -> [B,3,H,6W] (raw bytes: with ToTensor's /255)."""
     views = as_view_batch(views)
+    if views.dtype == torch.uint8:
+        return stitch_u8(views)
     B, _, _, H, W = views.shape
     out = torch.empty(B, 3, H, 6 * W, dtype=torch.float32, device=views.device)
     call("dd_stitch_f32", views.data_ptr(), out.data_ptr(), B, H, W, stream_ptr())
@@ -118,6 +121,9 @@ class EncoderConvStack(torch.autograd.Function):
     def forward(ctx, inp, w1, b1, w2, b2, w3, b3, act_dtype, c3_only, impl):
         _require_cuda(inp, w1, w2, w3)
         inp = _c(inp)
+        if inp.dtype == torch.uint8 and (act_dtype != torch.bfloat16 or impl == _lib.IMPL_SIMT):
+            # raw camera bytes on the fp32 parity path: ToTensor's /255 (and the stitch) as a pass of their own, bit-identical
+            inp = stitch_u8(inp) if inp.dim() == 5 else inp.float() / 255
         is_views = inp.dim() == 5
         if is_views:
             B, _, _, H, W = inp.shape
@@ -127,8 +133,9 @@ class EncoderConvStack(torch.autograd.Function):
         dev, code, st = inp.device, dtype_code(act_dtype), stream_ptr()
         H3, W3 = (H - 1) // 2 + 1, (Wm - 1) // 2 + 1
         w1, b1, w2, b2, w3, b3 = (_c(t.detach().float()) for t in (w1, b1, w2, b2, w3, b3))
+        in_flags = (_lib.IN_VIEWS if is_views else 0) | (_lib.IN_U8 if inp.dtype == torch.uint8 else 0)
         a1 = torch.empty(B, H, Wm, 32, dtype=act_dtype, device=dev)
-        call("dd_conv_c1_fwd", inp.data_ptr(), int(is_views), w1.data_ptr(), b1.data_ptr(), a1.data_ptr(), code,
+        call("dd_conv_c1_fwd", inp.data_ptr(), in_flags, w1.data_ptr(), b1.data_ptr(), a1.data_ptr(), code,
              B, H, Wm, impl, st)
         a2 = torch.empty_like(a1)
         call("dd_conv3x3_c32_fwd", a1.data_ptr(), w2.data_ptr(), b2.data_ptr(), a2.data_ptr(), code, B, H, Wm, 1,
@@ -144,7 +151,7 @@ class EncoderConvStack(torch.autograd.Function):
         else:
             out = torch.empty(B, 8 * H3 * W3, dtype=act_dtype, device=dev)
             call("dd_pool4_fwd", a3.data_ptr(), out.data_ptr(), code, B, H3, W3, st)
-        ctx.geom = (B, H, Wm, H3, W3, is_views, code, c3_only, impl, act_dtype)
+        ctx.geom = (B, H, Wm, H3, W3, in_flags, code, c3_only, impl, act_dtype)
         ctx.save_for_backward(inp, w2, w3, a1, a2, a3)
         return out
 
@@ -156,7 +163,7 @@ class EncoderConvStack(torch.autograd.Function):
             raise NotImplementedError("encoder_conv_stack: the camera views / mosaic require grad, but the scene pipeline "
                                       "has no input gradient for the first conv")
         inp, w2, w3, a1, a2, a3 = ctx.saved_tensors
-        B, H, Wm, H3, W3, is_views, code, c3_only, impl, act_dtype = ctx.geom
+        B, H, Wm, H3, W3, in_flags, code, c3_only, impl, act_dtype = ctx.geom
         dev, st = g.device, stream_ptr()
         ws, ws_n = _conv_ws(dev)
         da3 = torch.empty_like(a3)
@@ -186,7 +193,7 @@ class EncoderConvStack(torch.autograd.Function):
              impl, st)
         del da2
         dw1, db1 = torch.empty(32, 3, 3, 3, **f32), torch.empty(32, **f32)
-        call("dd_conv_c1_wgrad", inp.data_ptr(), int(is_views), da1.data_ptr(), code, dw1.data_ptr(), db1.data_ptr(),
+        call("dd_conv_c1_wgrad", inp.data_ptr(), in_flags, da1.data_ptr(), code, dw1.data_ptr(), db1.data_ptr(),
              ws.data_ptr(), ws_n, B, H, Wm, impl, st)
         return None, dw1, db1, dw2, db2, dw3, db3, None, None, None
 

@@ -16,6 +16,15 @@ def scene_batch(batch: int, view_h: int = 256, view_w: int = 306, map_hw: int = 
     return views, road
 
 
+def scene_batch_bytes(batch: int, view_h: int = 256, view_w: int = 306, map_hw: int = 800, seed: int = 20200505):
+    """The same synthetic scenes as raw camera bytes: views uint8 [B,6,3,H,W] (what the JPEG decoder yields before
+    ToTensor, data_helper.py:109-114) and the bool road map."""
+    g = torch.Generator().manual_seed(seed)
+    views = torch.randint(0, 256, (batch, 6, 3, view_h, view_w), dtype=torch.uint8, generator=g)
+    road = torch.rand(batch, map_hw, map_hw, generator=g) > 0.5
+    return views, road
+
+
 def random_roadmap_model(hidden=256, latent=128, view_h=256, view_w=306, dtype="bf16", device="cuda:0",
                          map_size=800, seed=20200505, state_dict=None):
     """RoadMapBCE with torch-default random weights (or ``state_dict``), built the way the reference
