@@ -42,11 +42,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="scenes per GPU per step")
+    ap.add_argument("--config", default="roadmap", choices=["roadmap", "ae", "bb"],
+                    help="roadmap = BASELINE config 2 (the metric's config); ae = config 3; bb = config 4")
+    ap.add_argument("--batch", type=int, default=None, help="scenes per GPU per step (default: 32; ae: 64)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 64 if a.config == "ae" else 32
+    return a
 
 
 def peaks():
@@ -324,6 +329,77 @@ def verify_data_parallel_step(model, opt, step, views, road, world):
                        "all-reduced mean gradient", "tolerance": 5e-6, "ok": worst == 0.0 and err_w < 5e-6}
 
 
+# ------------------------------------------------------------------------------------------------
+# workloads: BASELINE.json configs 2 (default, the metric's config), 3 and 4
+# ------------------------------------------------------------------------------------------------
+class Roadmap:
+    """config 2: RoadMapBCE train step (roadmap_bce_v2.py:83-133), bf16, hidden 256 / latent 128."""
+    key, metric = "roadmap", METRIC
+
+    def __init__(self, args, dev, rank):
+        from driving_dirty_b200.synthetic import scene_batch_bytes
+        self.model = build_model(args.dtype, dev)
+        # raw camera bytes (uint8, what the JPEG decoder yields): ToTensor's /255 (data_helper.py:109-114) is folded into
+        # the first conv's loads, bit-identical to feeding bytes.float()/255 (test_raw_byte_front_end_on_the_model_path)
+        views, road = scene_batch_bytes(args.batch, VIEW_H, VIEW_W, seed=20200506 + rank)
+        self.host = [views.pin_memory(), road.pin_memory()]
+        self.host_f32 = [(views.float() / 255).pin_memory(), self.host[1]]   # what the reference's dataloader hands over
+        self.describe = (f"RoadMapBCE train step (BASELINE config 2), {args.batch} scenes/GPU/step, views 6x3x{VIEW_H}x{VIEW_W} as raw "
+                         f"camera bytes (uint8; /255 folded into conv 1), hidden {HIDDEN} latent {LATENT}, map {MAP}x{MAP}, encoder unfrozen")
+
+    def loss(self, dev_tensors):
+        views, road = dev_tensors
+        return self.model.training_step((views, None, road), 1)["loss"]
+
+
+class AutoEncoder:
+    """config 3: BasicAE self-supervised pretraining step (autoencoder.py:78-108): stitch + mask one view, encoder,
+    decoder (2 dense blocks + 4 transposed convs), MSE."""
+    key, metric = "ae", "6-view scenes/sec, BasicAE pretraining step (six-to-one task: fwd + MSE + bwd + Adam)"
+
+    def __init__(self, args, dev, rank):
+        from driving_dirty_b200.synthetic import random_ae_model, scene_batch
+        self.model = random_ae_model(HIDDEN, LATENT, VIEW_H, VIEW_W, dtype=args.dtype, device=dev)
+        self.model.train()
+        views, _ = scene_batch(args.batch, VIEW_H, VIEW_W, map_hw=8, seed=20200506 + rank)
+        self.host = [views.pin_memory()]
+        self.host_f32 = None
+        self.describe = (f"BasicAE train step (BASELINE config 3), {args.batch} scenes/GPU/step, views 6x3x{VIEW_H}x{VIEW_W} fp32, "
+                         f"hidden {HIDDEN} latent {LATENT}, decoder to 3x{VIEW_H}x{VIEW_W}")
+
+    def loss(self, dev_tensors):
+        return self.model.training_step(dev_tensors[0], 1)["loss"]
+
+
+class BoundingBox:
+    """config 4: BBSpatialRoadMap step (spatial_w_rm.py:67-133): six strip convs + encoder convs (c3_only) + merging CNN
+    (four dilated transposed convs to 400x400, k2 s2 to 800x800), probability-space BCE.  The box targets are rasterised
+    ahead of time (the reference rasterises with PIL inside _run_step, :85-95: host work, not part of the device path)."""
+    key, metric = "bb", "6-view scenes/sec, BBSpatialRoadMap train step (fwd + BCE + bwd + Adam)"
+
+    def __init__(self, args, dev, rank):
+        import numpy as np
+        from driving_dirty_b200.synthetic import box_batch, random_bb_model, scene_batch
+        from driving_dirty_b200.utils.bb_to_img import boxes_to_binary_map
+        self.model = random_bb_model(HIDDEN, LATENT, dtype=args.dtype, device=dev)
+        self.model.frozen = False
+        self.model.ae.unfreeze()
+        self.model.train()
+        views, road = scene_batch(args.batch, VIEW_H, VIEW_W, seed=20200506 + rank)
+        raster = torch.from_numpy(np.stack([boxes_to_binary_map(b).copy() for b in box_batch(args.batch, 20200507 + rank)])).float()
+        self.host = [views.pin_memory(), road.pin_memory(), raster.pin_memory()]
+        self.host_f32 = None
+        self.describe = (f"BBSpatialRoadMap train step (BASELINE config 4), {args.batch} scenes/GPU/step, views 6x3x{VIEW_H}x{VIEW_W} fp32, "
+                         f"road map + box raster {MAP}x{MAP}, hidden {HIDDEN} latent {LATENT}, encoder unfrozen")
+
+    def loss(self, dev_tensors):
+        views, road, raster = dev_tensors
+        return self.model.training_step((views, raster, road), 1)["loss"]
+
+
+WORKLOADS = {w.key: w for w in (Roadmap, AutoEncoder, BoundingBox)}
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -336,29 +412,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from driving_dirty_b200 import _lib
     from driving_dirty_b200.optim import FusedAdam
-    from driving_dirty_b200.synthetic import scene_batch_bytes
 
     B = args.batch
-    model = build_model(args.dtype, dev)
+    wl = WORKLOADS[args.config](args, dev, rank)
+    model = wl.model
     params = [p for p in model.parameters() if p.requires_grad]
-    # world 1: one fused launch per tensor; world N: the two wide FC weights are reduced, updated and all-gathered by
-    # ONE kernel over NVLink peer memory (optim.FusedAdam / csrc/adam.cu), the small tensors by one flat NCCL all-reduce
+    # world 1: one fused launch per tensor; world N: the wide FC weights are reduced, updated and all-gathered by ONE kernel
+    # over NVLink peer memory (optim.FusedAdam / csrc/adam.cu), launched from the backward pass; the small tensors share
+    # one flat sharded bucket
     opt = FusedAdam(params, lr=1e-3, overlap_backward=True)
+    resident = [t.to(dev, non_blocking=True) for t in wl.host]
 
-    # synthetic scenes: a different batch per rank, pinned on the host, one resident copy in HBM.  The views are raw
-    # camera bytes (uint8, what the JPEG decoder yields): ToTensor's /255 (data_helper.py:109-114) is folded into the first
-    # conv's loads, bit-identical to feeding bytes.float()/255 (tests/test_modules_gpu.py::test_raw_byte_front_end_...).
-    views_h, road_h = scene_batch_bytes(B, VIEW_H, VIEW_W, seed=20200506 + rank)
-    views_h, road_h = views_h.pin_memory(), road_h.pin_memory()
-    views_d, road_d = views_h.to(dev, non_blocking=True), road_h.to(dev, non_blocking=True)
-    views_f32_h = (views_h.float() / 255).pin_memory()      # what the reference's dataloader hands over (for e2e_f32_views)
-
-    def step(views, road):
+    def step(tensors):
         opt.zero_grad(set_to_none=True)
-        out = model.training_step((views, None, road), 1)
-        out["loss"].backward()
+        loss = wl.loss(tensors)
+        loss.backward()
         opt.step()
-        return out["loss"]
+        return loss
 
     def barrier():
         if world > 1:
@@ -369,7 +439,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None      # up and polling before the GPU work starts
     # >= 5 untimed steps: the first ones map the symmetric / multicast buffers and size the allocator's pools
     for _ in range(max(args.warmup, 5)):
-        step(views_d, road_d)
+        step(resident)
     barrier()
     if sampler:
         sampler.mark()
@@ -377,25 +447,26 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = step(views_d, road_d)
+        loss = step(resident)
     e1.record()
     barrier()
     launches = _lib.launch_count() - l0
     sec = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.stop() if sampler else None
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # ---- end to end: host buffers in, loss out, every step -------------------------------------
     copy_stream = torch.cuda.Stream()
-    bufs = [(torch.empty_like(views_d), torch.empty_like(road_d)) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     loss_h = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def e2e_time(src_views, bufs):
+    def e2e_time(host):
+        bufs = [[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host] for _ in range(2)]
+
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
-                bufs[i][0].copy_(src_views, non_blocking=True)
-                bufs[i][1].copy_(road_h, non_blocking=True)
+                for d, h in zip(bufs[i], host):
+                    d.copy_(h, non_blocking=True)
                 ready[i].record(copy_stream)
 
         def e2e_loop(k):
@@ -406,7 +477,7 @@ def run_ours(args):
                 if i + 1 < k:
                     copy_stream.wait_stream(torch.cuda.current_stream())   # buffer (i+1)&1 was consumed by step i-1
                     prefetch((i + 1) & 1)
-                l = step(bufs[cur][0], bufs[cur][1])
+                l = step(bufs[cur])
                 loss_h.copy_(l.detach(), non_blocking=False)               # D2H read of the step's result
 
         e2e_loop(2)
@@ -417,51 +488,53 @@ def run_ours(args):
         barrier()
         return e0.elapsed_time(e1) * 1e-3
 
-    sec_e2e = e2e_time(views_h, bufs)
-    bufs32 = [(torch.empty(views_f32_h.shape, device=dev), torch.empty_like(road_d)) for _ in range(2)]
-    sec_e2e_f32 = e2e_time(views_f32_h, bufs32)
-    del bufs32
+    sec_e2e = e2e_time(wl.host)
+    sec_e2e_f32 = e2e_time(wl.host_f32) if wl.host_f32 is not None else 0.0
 
     t = torch.tensor([sec, sec_e2e, sec_e2e_f32], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sec, sec_e2e, sec_e2e_f32 = float(t[0]), float(t[1]), float(t[2])
-    verify = verify_data_parallel_step(model, opt, step, views_d, road_d, world) if world > 1 else None
-    if verify is not None and not verify["ok"]:
-        raise SystemExit(f"bench.py: the data-parallel step failed its self-check: {json.dumps(verify)}")
+    verify = None
+    if world > 1 and args.config == "roadmap":
+        verify = verify_data_parallel_step(model, opt, lambda v, r: step([v, r]), resident[0], resident[1], world)
+        if verify is not None and not verify["ok"]:
+            raise SystemExit(f"bench.py: the data-parallel step failed its self-check: {json.dumps(verify)}")
 
     if rank == 0:
         pk, pk_src = peaks()
         adt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-        del bufs
         torch.cuda.empty_cache()
-        roof = dominant_kernel_roofline(B, adt, pk, pk_src)
-        hbm_rows = hbm_kernel_rooflines(B, pk)
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            sps, csec = cpu_train_steps(args.cpu_batch, 3, 1)
-            cpu = {"value": sps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"3 steps of B={args.cpu_batch} scenes (fwd+BCE+TS+bwd+Adam) through oracle/scene_oracle.py "
-                             f"(torch CPU ops), {os.cpu_count()} threads, {csec:.2f} s/step"}
+        roof, hbm_rows, cpu = None, None, None
+        if args.config == "roadmap":
+            roof = dominant_kernel_roofline(B, adt, pk, pk_src)
+            hbm_rows = hbm_kernel_rooflines(B, pk)
+            if world == 1 and not args.no_cpu_baseline:
+                sps, csec = cpu_train_steps(args.cpu_batch, 3, 1)
+                cpu = {"value": sps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                       "sample": f"3 steps of B={args.cpu_batch} scenes (fwd+BCE+TS+bwd+Adam) through oracle/scene_oracle.py "
+                                 f"(torch CPU ops: the arithmetic the reference executes; not the imported reference, which "
+                                 f"does not travel to the GPU box), {os.cpu_count()} threads, {csec:.2f} s/step"}
         total = B * world * args.steps
+        h2d = sum(t.numel() * t.element_size() for t in wl.host)
         line = {
-            "metric": METRIC, "value": total / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": wl.metric, "value": total / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 5), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"RoadMapBCE train step (BASELINE config 2), {B} scenes/GPU/step, views 6x3x{VIEW_H}x{VIEW_W}, "
-                                   f"hidden {HIDDEN} latent {LATENT}, map {MAP}x{MAP}, views as raw camera bytes (uint8; /255 folded into conv 1), encoder unfrozen, Adam (dd_adam_step" + (", sharded over NVLink peer memory" + (" + multicast" if opt.uses_multicast else "") if world > 1 else "") + ")",
+            "config": {"workload": wl.describe + ", Adam (dd_adam_step" + (", sharded over NVLink peer memory" + (" + multicast" if opt.uses_multicast else "") if world > 1 else "") + ")",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "activations (2 x 963 MB per layer) and the 1.3 GB of FC weights exceed the 126 MB L2 many times over; no explicit flush"},
-            "e2e": {"value": total / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": views_h.numel() + road_h.numel(),
-                    "d2h_bytes_per_step": 4, "ms_per_step": sec_e2e / args.steps * 1e3,
-                    "note": "pinned host views (raw camera bytes, uint8) and bool road maps copied every step on a side stream "
-                            "(double-buffered), loss read back"},
-            "e2e_f32_views": {"value": total / sec_e2e_f32, "unit": UNIT, "h2d_bytes_per_step": views_f32_h.numel() * 4 + road_h.numel(),
-                              "d2h_bytes_per_step": 4, "ms_per_step": sec_e2e_f32 / args.steps * 1e3,
-                              "note": "the same with fp32 host views (what the reference's ToTensor dataloader emits): 4x the H2D bytes"},
+                       "l2": "activations (GBs per layer) and the FC weights exceed the 126 MB L2 many times over; no explicit flush"},
+            "e2e": {"value": total / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": sec_e2e / args.steps * 1e3,
+                    "note": "pinned host inputs copied every step on a side stream (double-buffered), loss read back"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_rows,
             "cpu_baseline": cpu, "final_loss": final_loss,
         }
+        if wl.host_f32 is not None:
+            line["e2e_f32_views"] = {"value": total / sec_e2e_f32, "unit": UNIT,
+                                     "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in wl.host_f32),
+                                     "d2h_bytes_per_step": 4, "ms_per_step": sec_e2e_f32 / args.steps * 1e3,
+                                     "note": "the same with fp32 host views (what the reference's ToTensor dataloader emits): 4x the view bytes"}
         if verify is not None:
             line["dp_self_check"] = verify
         print(json.dumps(line), flush=True)

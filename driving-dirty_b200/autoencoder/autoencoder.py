@@ -76,7 +76,7 @@ class BasicAE(LightningModule):
         return {"val_loss": avg_val_loss, "log": {"avg_val_loss": avg_val_loss}}
 
     def configure_optimizers(self):
-        from ...optim import make_adam
+        from ..optim import make_adam
         return make_adam(self, self.hparams.learning_rate)
 
     @staticmethod

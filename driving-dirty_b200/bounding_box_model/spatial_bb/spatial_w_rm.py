@@ -60,7 +60,10 @@ class BBSpatialRoadMap(LightningModule):
     def _run_step(self, batch, batch_idx, step_name):
         sample, target, road_image = batch
         sample = ops.as_view_batch(sample)
-        target_bb_img = self.bb_coord_to_map(target).to(device=sample.device, dtype=torch.float32)
+        # `target`: the dataloader's tuple of dicts (rasterised here on the host like the reference, :85-95), or -- an
+        # extension for loaders that rasterise ahead of time -- the [B,800,800] raster itself
+        target_bb_img = (target if torch.is_tensor(target) else self.bb_coord_to_map(target)).to(device=sample.device,
+                                                                                              dtype=torch.float32)
         rm = (road_image if torch.is_tensor(road_image) else torch.stack(tuple(road_image), dim=0)).float().unsqueeze(1)
         pred_bb_img = self(sample, rm)
         if batch_idx % self.hparams.output_img_freq == 0 and self.logger is not None:
@@ -97,7 +100,7 @@ class BBSpatialRoadMap(LightningModule):
         return {"val_loss": avg_val_loss, "log": {"avg_val_loss": avg_val_loss}}
 
     def configure_optimizers(self):
-        from ....optim import make_adam
+        from ...optim import make_adam
         return make_adam(self, self.hparams.learning_rate)
 
     @staticmethod

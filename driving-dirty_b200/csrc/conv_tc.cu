@@ -838,10 +838,15 @@ struct C1Bars {
 };
 
 // pointer to channel 0 of (b, mosaic row h, mosaic column wm); channel stride returned in cstride
-template <typename TIN> __device__ __forceinline__ float c1_ld(const TIN* p);
-template <> __device__ __forceinline__ float c1_ld<float>(const float* p) { return __ldg(p); }
-// torchvision ToTensor (data_helper.py:109-114): byte -> float32, divided by 255 (IEEE division: bit-identical)
-template <> __device__ __forceinline__ float c1_ld<uint8_t>(const uint8_t* p) { return __fdiv_rn((float)__ldg(p), 255.0f); }
+// torchvision ToTensor (data_helper.py:109-114): byte -> float32, divided by 255.  The IEEE division (bit-identical to
+// x.float() / 255) is done ONCE per CTA for the 256 possible bytes into a shared-memory table; a division per pixel
+// made the raw-byte kernels instruction-bound (the c1 forward + weight gradient pair ran 1.6 ms slower per step).
+template <typename TIN> __device__ __forceinline__ float c1_ld(const TIN* p, const float* lut);
+template <> __device__ __forceinline__ float c1_ld<float>(const float* p, const float*) { return __ldg(p); }
+template <> __device__ __forceinline__ float c1_ld<uint8_t>(const uint8_t* p, const float* lut) { return lut[__ldg(p)]; }
+__device__ __forceinline__ void c1_fill_lut(float* lut) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
+}
 
 template <bool IS_VIEWS, typename TIN>
 __device__ __forceinline__ const TIN* c1_src(const TIN* __restrict__ in, int b, int h, int wm, int H, int Wm,
@@ -859,7 +864,7 @@ __device__ __forceinline__ const TIN* c1_src(const TIN* __restrict__ in, int b, 
 // one input row -> [pixel][8 ch] bf16 plane (130 pixels), by one warp
 template <bool IS_VIEWS, typename TIN>
 __device__ __forceinline__ void c1_load_row(uint8_t* __restrict__ slab, const TIN* __restrict__ in, int b, int r, int c0,
-                                            int H, int Wm, int lane) {
+                                            int H, int Wm, int lane, const float* lut) {
   float v[5][3];
   bool ok[5];
 #pragma unroll
@@ -869,7 +874,7 @@ __device__ __forceinline__ void c1_load_row(uint8_t* __restrict__ slab, const TI
     if (ok[k]) {
       size_t cs;
       const TIN* p = c1_src<IS_VIEWS, TIN>(in, b, r, col, H, Wm, cs);
-      v[k][0] = c1_ld<TIN>(p); v[k][1] = c1_ld<TIN>(p + cs); v[k][2] = c1_ld<TIN>(p + 2 * cs);
+      v[k][0] = c1_ld<TIN>(p, lut); v[k][1] = c1_ld<TIN>(p + cs, lut); v[k][2] = c1_ld<TIN>(p + 2 * cs, lut);
     } else {
       v[k][0] = v[k][1] = v[k][2] = 0.f;
     }
@@ -897,6 +902,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __
   uint8_t* s_slab = smem + C1_WBYTES;
   C1Bars* bars = reinterpret_cast<C1Bars*>(smem + C1_WBYTES + C1_RING * PS);
   __shared__ float s_bias[C];
+  __shared__ float s_lut[256];
+  c1_fill_lut(s_lut);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int wtiles = (Wm + TILE_M - 1) / TILE_M;
@@ -935,7 +942,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __
         if ((g % C1_NPROD) != (uint32_t)warp) continue;
         const uint32_t slot = g % C1_RING;
         umma::mbar_wait(&bars->empty[slot], ((g / C1_RING) & 1) ^ 1);
-        c1_load_row<IS_VIEWS, TIN>(s_slab + slot * PS, in, b, h0 - 1 + sidx, wt * TILE_M - 1, H, Wm, lane);
+        c1_load_row<IS_VIEWS, TIN>(s_slab + slot * PS, in, b, h0 - 1 + sidx, wt * TILE_M - 1, H, Wm, lane, s_lut);
         umma::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(&bars->full[slot]);

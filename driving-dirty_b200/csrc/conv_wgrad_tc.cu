@@ -300,10 +300,15 @@ constexpr int C1_PARTIAL = C1_RB * 3 * 10 * C;  // floats per CTA: [q][kh][j][co
 constexpr int C1_THREADS = 192;
 static_assert(C1_SMEM <= 227 * 1024, "shared memory");
 
-template <typename TIN> __device__ __forceinline__ float c1_ld(const TIN* p);
-template <> __device__ __forceinline__ float c1_ld<float>(const float* p) { return __ldg(p); }
-// torchvision ToTensor (data_helper.py:109-114): byte -> float32, divided by 255 (IEEE division: bit-identical)
-template <> __device__ __forceinline__ float c1_ld<uint8_t>(const uint8_t* p) { return __fdiv_rn((float)__ldg(p), 255.0f); }
+// torchvision ToTensor (data_helper.py:109-114): byte -> float32, divided by 255.  The IEEE division (bit-identical to
+// x.float() / 255) is done ONCE per CTA for the 256 possible bytes into a shared-memory table; a division per pixel
+// made the raw-byte kernels instruction-bound (the c1 forward + weight gradient pair ran 1.6 ms slower per step).
+template <typename TIN> __device__ __forceinline__ float c1_ld(const TIN* p, const float* lut);
+template <> __device__ __forceinline__ float c1_ld<float>(const float* p, const float*) { return __ldg(p); }
+template <> __device__ __forceinline__ float c1_ld<uint8_t>(const uint8_t* p, const float* lut) { return lut[__ldg(p)]; }
+__device__ __forceinline__ void c1_fill_lut(float* lut) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
+}
 
 template <bool IS_VIEWS, typename TIN>
 __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_wgrad_ring_kernel(const TIN* __restrict__ in,
@@ -313,6 +318,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_wgrad_ring_kernel(const
   uint8_t* s_x = smem;
   uint8_t* s_d = smem + C1_XBYTES;
   RingBars* bars = reinterpret_cast<RingBars*>(smem + C1_XBYTES + C1_DBYTES);
+  __shared__ float s_lut[256];
+  c1_fill_lut(s_lut);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int wtiles = (Wm + KP - 1) / KP;
@@ -374,8 +381,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_wgrad_ring_kernel(const
         const bool row_ok = row >= 0 && row < H;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          v[r][ch] = (row_ok && c.cok) ? c1_ld<TIN>(in + c.coff + ch * cstride + (size_t)row * Wv) : 0.f;
-          e[r][ch] = (has_edge && row_ok && c.eok) ? c1_ld<TIN>(in + c.eoff + ch * cstride + (size_t)row * Wv) : 0.f;
+          v[r][ch] = (row_ok && c.cok) ? c1_ld<TIN>(in + c.coff + ch * cstride + (size_t)row * Wv, s_lut) : 0.f;
+          e[r][ch] = (has_edge && row_ok && c.eok) ? c1_ld<TIN>(in + c.eoff + ch * cstride + (size_t)row * Wv, s_lut) : 0.f;
         }
       }
     };

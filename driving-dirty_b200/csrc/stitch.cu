@@ -77,6 +77,25 @@ __global__ void __launch_bounds__(256) stitch_scalar_kernel(const TIN* __restric
   }
 }
 
+// ToTensor as a pass of its own (data_helper.py:109-114): out[i] = float(in[i]) / 255, bit-identical (the IEEE division is
+// done once per CTA for the 256 possible bytes).  16 bytes in, four 16-byte stores out per thread and iteration.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, long long n) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  __syncthreads();
+  const long long n16 = n >> 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      __stcs(reinterpret_cast<float4*>(out) + 4 * i + k,
+             make_float4(lut[w[k] & 255u], lut[(w[k] >> 8) & 255u], lut[(w[k] >> 16) & 255u], lut[w[k] >> 24]));
+  }
+  for (long long i = (n16 << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = lut[in[i]];
+}
+
 int launch_stitch(const float* views, float* x, float* y, int B, int H, int W, int slot, int mode,
                   cudaStream_t st) {
   const int rows = B * 3 * H;
@@ -120,4 +139,15 @@ extern "C" int dd_stitch_u8(const uint8_t* views, float* mosaic, int B, int H, i
   int grid = (int)((total + 255) / 256 < dd::kSMs * 8 ? (total + 255) / 256 : dd::kSMs * 8);
   stitch_scalar_kernel<0, uint8_t><<<grid, 256, 0, dd::as_stream(stream)>>>(views, mosaic, nullptr, B, H, W, -1);
   return dd::check_launch("stitch_u8");
+}
+
+extern "C" int dd_u8_to_f32(const uint8_t* in, float* out, long long n, void* stream) {
+  DD_REQUIRE(n >= 0, DD_ERR_BAD_ARG, "dd_u8_to_f32: n=%lld", n);
+  if (n == 0) return 0;
+  DD_REQUIRE(in && out, DD_ERR_BAD_ARG, "dd_u8_to_f32: null pointer");
+  DD_REQUIRE((uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0, DD_ERR_ALIGNMENT, "dd_u8_to_f32: pointers must be 16-byte aligned");
+  const long long want = ((n >> 4) + 255) / 256;
+  const int grid = (int)(want < 1 ? 1 : (want < dd::kSMs * 8 ? want : dd::kSMs * 8));
+  u8_to_f32_kernel<<<grid, 256, 0, dd::as_stream(stream)>>>(in, out, n);
+  return dd::check_launch("u8_to_f32");
 }

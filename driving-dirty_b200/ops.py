@@ -51,8 +51,9 @@ _ws = _Workspaces()
 # --------------------------------------------------------------------------------------------
 def as_view_batch(sample) -> torch.Tensor:
     """tuple/list of B [6,3,H,W] tensors (what collate_fn yields) or a [B,6,3,H,W] tensor ->
-    contiguous [B,6,3,H,W] CUDA tensor, without a copy when the tuple is ``batch.unbind(0)``: fp32 in [0,1] (what
-    ToTensor hands the reference) or uint8 raw camera bytes (the /255 is then folded into the first conv's loads)."""
+    contiguous [B,6,3,H,W] fp32 CUDA tensor, without a copy when the tuple is ``batch.unbind(0)``.  uint8 raw camera
+    bytes are taken as they come off the JPEG decoder: ToTensor's /255 (data_helper.py:109-114) runs here on the device
+    (``dd_u8_to_f32``, bit-identical to ``x.float() / 255``), so only a quarter of the bytes cross PCIe."""
     if torch.is_tensor(sample):
         x = sample
     else:
@@ -66,16 +67,27 @@ def as_view_batch(sample) -> torch.Tensor:
     _require_cuda(x)
     if x.dim() != 5 or x.shape[1] != 6 or x.shape[2] != 3:
         raise RuntimeError(f"expected views of shape [B,6,3,H,W], got {tuple(x.shape)}")
-    if x.dtype not in (torch.float32, torch.uint8):
+    if x.dtype == torch.uint8:
+        return bytes_to_float(x)
+    if x.dtype != torch.float32:
         x = x.float()
     return _c(x)
 
 
+def bytes_to_float(x_u8: torch.Tensor) -> torch.Tensor:
+    """torchvision ToTensor's scaling on the device: uint8 -> float32 / 255 (any shape), bit-identical."""
+    _require_cuda(x_u8)
+    x_u8 = _c(x_u8)
+    out = torch.empty(x_u8.shape, dtype=torch.float32, device=x_u8.device)
+    call("dd_u8_to_f32", x_u8.data_ptr(), out.data_ptr(), x_u8.numel(), stream_ptr())
+    return out
+
+
 def stitch(views: torch.Tensor) -> torch.Tensor:
     """wide_stitch_six_images (roadmap_bce_v2.py:53-64): [B,6,3,H,W] -> [B,3,H,6W] (raw bytes: with ToTensor's /255)."""
-    views = as_view_batch(views)
-    if views.dtype == torch.uint8:
+    if torch.is_tensor(views) and views.dtype == torch.uint8:
         return stitch_u8(views)
+    views = as_view_batch(views)
     B, _, _, H, W = views.shape
     out = torch.empty(B, 3, H, 6 * W, dtype=torch.float32, device=views.device)
     call("dd_stitch_f32", views.data_ptr(), out.data_ptr(), B, H, W, stream_ptr())
@@ -121,9 +133,11 @@ class EncoderConvStack(torch.autograd.Function):
     def forward(ctx, inp, w1, b1, w2, b2, w3, b3, act_dtype, c3_only, impl):
         _require_cuda(inp, w1, w2, w3)
         inp = _c(inp)
-        if inp.dtype == torch.uint8 and (act_dtype != torch.bfloat16 or impl == _lib.IMPL_SIMT):
-            # raw camera bytes on the fp32 parity path: ToTensor's /255 (and the stitch) as a pass of their own, bit-identical
-            inp = stitch_u8(inp) if inp.dim() == 5 else inp.float() / 255
+        if inp.dtype == torch.uint8:
+            # raw camera bytes: ToTensor's /255 as a pass of its own (0.04 ms for 32 scenes).  The c1 kernels can also read
+            # bytes directly (DD_IN_U8, bit-identical, tested), but their byte-granular loads keep too few bytes in flight:
+            # +0.26 ms per step measured (profiles/r2_kernel_times.txt), so the model path converts first.
+            inp = bytes_to_float(inp)
         is_views = inp.dim() == 5
         if is_views:
             B, _, _, H, W = inp.shape

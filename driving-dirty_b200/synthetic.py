@@ -48,3 +48,42 @@ def random_roadmap_model(hidden=256, latent=128, view_h=256, view_w=306, dtype="
         res = model.load_state_dict({k: v.clone() for k, v in state_dict.items()}, strict=True)
         assert not res.missing_keys and not res.unexpected_keys
     return model.to(device)
+
+
+def box_batch(batch: int, seed: int = 20200507):
+    """Synthetic object boxes: per scene 5-20 axis-aligned 4.6 m x 2 m boxes with centres U(-30, 30) m, in
+    the dataset's convention [N,2,4] (metres; rows x / y; columns fl, fr, bl, br; data_helper.py:118,129)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(batch):
+        n = int(torch.randint(5, 21, (1,), generator=g))
+        c = torch.rand(n, 2, generator=g) * 60 - 30
+        xs = torch.stack([c[:, 0] + 2.3, c[:, 0] + 2.3, c[:, 0] - 2.3, c[:, 0] - 2.3], dim=1)
+        ys = torch.stack([c[:, 1] + 1.0, c[:, 1] - 1.0, c[:, 1] + 1.0, c[:, 1] - 1.0], dim=1)
+        out.append(torch.stack([xs, ys], dim=1))
+    return out
+
+
+def random_ae_model(hidden=256, latent=128, view_h=256, view_w=306, dtype="bf16", device="cuda:0", seed=20200505):
+    """BasicAE (autoencoder.py) with torch-default random weights."""
+    from .autoencoder.autoencoder import BasicAE, default_hparams
+    torch.manual_seed(seed)
+    hp = default_hparams(hidden_dim=hidden, latent_dim=latent, input_width=6 * view_w, input_height=view_h,
+                         output_width=view_w, output_height=view_h, compute_dtype=dtype)
+    return BasicAE(hp).to(device)
+
+
+def random_bb_model(hidden=256, latent=128, dtype="bf16", device="cuda:0", seed=20200505):
+    """BBSpatialRoadMap (spatial_w_rm.py) with torch-default random weights, built through an AE checkpoint on disk like
+    the reference demands (spatial_w_rm.py:44)."""
+    from .autoencoder.autoencoder import BasicAE, default_hparams
+    from .bounding_box_model.spatial_bb.spatial_w_rm import BBSpatialRoadMap
+    from .lightning_compat import save_checkpoint
+    torch.manual_seed(seed)
+    hp = default_hparams(hidden_dim=hidden, latent_dim=latent, compute_dtype=dtype)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ae.ckpt")
+        save_checkpoint(BasicAE(hp), path)
+        model = BBSpatialRoadMap(Namespace(pretrained_path=path, learning_rate=1e-3, batch_size=4, output_img_freq=10 ** 9,
+                                           unfreeze_epoch_no=0, link="", mse_loss=False, compute_dtype=dtype))
+    return model.to(device)

@@ -58,6 +58,8 @@ int dd_stitch_mask_f32(const float* views, float* x, float* y, int B, int H, int
 /* Front-end for raw camera bytes (data_helper.py:109-114 ToTensor): views u8 [B,6,3,H,W] ->
  * mosaic f32 with value/255 (bit-identical to x.float()/255). */
 int dd_stitch_u8(const uint8_t* views, float* mosaic, int B, int H, int W, void* stream);
+/* ToTensor alone (data_helper.py:113): out[i] = float(in[i]) / 255, bit-identical, n elements of any layout. */
+int dd_u8_to_f32(const uint8_t* in, float* out, long long n, void* stream);
 
 /* ---- A3: encoder convs (components.py:19-21,41-43) ------------------------------------------
  * c1: 3->32, 3x3, pad 1, + bias + ReLU.  `in` is either the views [B,6,3,H,W] (in_flags &

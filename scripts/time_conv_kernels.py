@@ -7,6 +7,7 @@ from driving_dirty_b200._lib import call, stream_ptr
 B, H, W = int(os.environ.get("B", 32)), 256, 1836
 dev = torch.device("cuda")
 views = torch.rand(B, 6, 3, 256, 306, device=dev)
+views_u8 = torch.randint(0, 256, (B, 6, 3, 256, 306), device=dev, dtype=torch.uint8)
 x = torch.rand(B, H, W, 32, device=dev).bfloat16()
 dy = (torch.rand(B, H, W, 32, device=dev) - 0.5).bfloat16()
 out = torch.empty_like(x)
@@ -24,6 +25,7 @@ GB = 1e9
 act = x.numel() * 2
 runs = {
     "c1 fwd   (views -> a1)": (lambda: call("dd_conv_c1_fwd", views.data_ptr(), 1, w1.data_ptr(), b.data_ptr(), out.data_ptr(), 1, B, H, W, 0, st), views.numel() * 4 + act),
+    "c1 fwd   (u8 views)": (lambda: call("dd_conv_c1_fwd", views_u8.data_ptr(), 3, w1.data_ptr(), b.data_ptr(), out.data_ptr(), 1, B, H, W, 0, st), views.numel() + act),
     "c2 fwd   (s1)": (lambda: call("dd_conv3x3_c32_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), 1, B, H, W, 1, 0, st), 2 * act),
     "c3 fwd   (s2)": (lambda: call("dd_conv3x3_c32_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), out3.data_ptr(), 1, B, H, W, 2, 0, st), act + act // 4),
     "c3 dgrad (s2)": (lambda: call("dd_conv3x3_c32_dgrad", dy3.data_ptr(), w.data_ptr(), x.data_ptr(), out.data_ptr(), 1, B, H, W, 2, 0, st), 2 * act + act // 4),
@@ -31,6 +33,7 @@ runs = {
     "c2 dgrad (s1)": (lambda: call("dd_conv3x3_c32_dgrad", dy.data_ptr(), w.data_ptr(), x.data_ptr(), out.data_ptr(), 1, B, H, W, 1, 0, st), 3 * act),
     "c2 wgrad (s1)": (lambda: call("dd_conv3x3_c32_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n, 1, B, H, W, 1, 0, st), 2 * act),
     "c1 wgrad": (lambda: call("dd_conv_c1_wgrad", views.data_ptr(), 1, dy.data_ptr(), 1, dw1.data_ptr(), db.data_ptr(), ws.data_ptr(), n, B, H, W, 0, st), views.numel() * 4 + act),
+    "c1 wgrad (u8 views)": (lambda: call("dd_conv_c1_wgrad", views_u8.data_ptr(), 3, dy.data_ptr(), 1, dw1.data_ptr(), db.data_ptr(), ws.data_ptr(), n, B, H, W, 0, st), views.numel() + act),
 }
 tot = 0.0
 for name, (fn, nbytes) in runs.items():
