@@ -42,15 +42,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="roadmap", choices=["roadmap", "ae", "bb"],
-                    help="roadmap = BASELINE config 2 (the metric's config); ae = config 3; bb = config 4")
+    ap.add_argument("--config", default="roadmap", choices=["roadmap", "ae", "bb", "inference"],
+                    help="roadmap = BASELINE config 2 (the metric's config); ae = config 3; bb = config 4; inference = config 5")
+    ap.add_argument("--mode", default=None, choices=[None, "inference", "train"], help="--mode inference == --config inference")
+    ap.add_argument("--parity-scenes", type=int, default=52, help="inference: scenes checked against the CPU oracle (0 = skip)")
     ap.add_argument("--batch", type=int, default=None, help="scenes per GPU per step (default: 32; ae: 64)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    if a.mode == "inference":
+        a.config = "inference"
     if a.batch is None:
-        a.batch = 64 if a.config == "ae" else 32
+        a.batch = 64 if a.config == "ae" else (256 if a.config == "inference" else 32)
     return a
 
 
@@ -399,6 +403,140 @@ class BoundingBox:
 
 WORKLOADS = {w.key: w for w in (Roadmap, AutoEncoder, BoundingBox)}
 
+FLOP_CONVS_PER_SCENE = 11.641e9       # c1 + c2 + c3 forward
+
+
+def run_inference(args):
+    """BASELINE config 5: ModelLoader.get_binary_road_map, batch sweep 1..256, bf16 tensor-core path and fp32 parity path,
+    device-resident and end to end (pinned host bytes in, binary maps out); replicas only, no collective.  Parity on rank
+    0 against the CPU oracle (oracle/scene_oracle.py, the reference's torch arithmetic) with identical dropout masks:
+    flipped pixels in ppm, the largest |reference logit| among the flipped ones, and the rounded threat score in
+    <= 26-scene chunks (the reference's fp32 sums are exact up to 26 scenes) against our integer counts."""
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from driving_dirty_b200 import _lib
+    from driving_dirty_b200.model_loader import ModelLoader
+    from driving_dirty_b200.synthetic import random_roadmap_model, scene_batch_bytes
+    m16 = random_roadmap_model(HIDDEN, LATENT, VIEW_H, VIEW_W, dtype="bf16", device=dev)
+    sd = {k: v.detach().clone() for k, v in m16.state_dict().items()}
+    m32 = random_roadmap_model(HIDDEN, LATENT, VIEW_H, VIEW_W, dtype="fp32", device=dev, state_dict=sd)
+    loaders = {"bf16": ModelLoader(m16, device=dev), "fp32": ModelLoader(m32, device=dev)}
+    bmax = args.batch if args.batch else 256
+    views_h, road_h = scene_batch_bytes(bmax, VIEW_H, VIEW_W, seed=20200506 + rank)
+    views_h = views_h.pin_memory()
+    views_d = views_h.to(dev)
+    sizes = [b for b in (1, 2, 4, 8, 16, 32, 64, 128, 256) if b <= bmax]
+    sampler = ClockSampler(local) if rank == 0 else None
+    sweep, l0 = [], _lib.launch_count()
+    if sampler:
+        sampler.mark()
+    for name, loader in loaders.items():
+        for b in sizes:
+            if name == "fp32" and b > 64:
+                continue                                  # the fp32 SIMT parity path is not the throughput path
+            iters = max(3, min(args.steps * 4, 256 // b))
+            row = {"dtype": name, "batch": b}
+            for mode, src in (("resident", views_d[:b]), ("e2e", views_h[:b])):
+                for _ in range(3):
+                    out = loader.get_binary_road_map(src)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    out = loader.get_binary_road_map(src)
+                    if mode == "e2e":
+                        out_h = out.to("cpu")              # binary maps back on the host, every call
+                e1.record()
+                torch.cuda.synchronize()
+                sec = e0.elapsed_time(e1) * 1e-3 / iters
+                row[mode + "_scenes_s"] = b / sec
+                row[mode + "_ms"] = sec * 1e3
+            sweep.append(row)
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count() - l0
+    best = max((r for r in sweep if r["dtype"] == "bf16"), key=lambda r: r["resident_scenes_s"])
+    t = torch.tensor([best["resident_scenes_s"], max(r["e2e_scenes_s"] for r in sweep if r["dtype"] == "bf16")], device=dev,
+                     dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)        # replicas only: the job's throughput is the sum over ranks
+    if rank == 0:
+        pk, pk_src = peaks()
+        parity = inference_parity(loaders, sd, min(bmax, args.parity_scenes)) if args.parity_scenes > 0 else None
+        line = {
+            "metric": "6-view scenes/sec, ModelLoader.get_binary_road_map (inference)", "value": float(t[0]), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": 3, "ms_per_step": best["resident_ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ModelLoader.get_binary_road_map (BASELINE config 5), batch sweep {sizes}, views 6x3x{VIEW_H}x{VIEW_W} raw "
+                                   f"camera bytes, hidden {HIDDEN} latent {LATENT}, map {MAP}x{MAP}; value = best batch ({best['batch']}), "
+                                   f"replicas only (sum over ranks); CUDA graph up to batch {loaders['bf16'].graph_max_batch}",
+                       "batch_per_gpu": best["batch"], "parallelism": f"replicas x{world}",
+                       "l2": "activations of the best batch exceed the 126 MB L2; small batches are L2 resident by nature"},
+            "e2e": {"value": float(t[1]), "unit": UNIT, "h2d_bytes_per_step": best["batch"] * 6 * 3 * VIEW_H * VIEW_W,
+                    "d2h_bytes_per_step": best["batch"] * MAP * MAP * 4,
+                    "note": "pinned host bytes staged by ModelLoader every call, float32 binary maps copied back to the host"},
+            "gpu_launches": int(launches), "clocks": clocks, "sweep": sweep,
+            "conv_stack": {"tflops_at_best_batch": FLOP_CONVS_PER_SCENE * best["resident_scenes_s"] / 1e12,
+                           "frac_of_bf16_peak": FLOP_CONVS_PER_SCENE * best["resident_scenes_s"] / 1e12 / pk["bf16_tflops"],
+                           "peak_source": pk_src, "note": "c1+c2+c3 forward flops over the WHOLE call's time (convs, pool, FC, head, sigmoid)"},
+            "parity_vs_oracle": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def inference_parity(loaders, state_dict, n):
+    """Binary maps of both paths against the oracle on n scenes with identical (CPU-generator) dropout masks."""
+    from oracle import scene_oracle as so
+    from tests.helpers import cpu_rng_dropout
+    torch.set_num_threads(os.cpu_count())
+    views, road = so.synthetic_scene_batch(n, VIEW_H, VIEW_W, seed=20200601)
+    params = {k: v.detach().cpu() for k, v in state_dict.items()}
+    res = {"scenes": n, "chunk": 26}
+    ref_logits, ref_bin = [], []
+    chunks = [(lo, min(lo + 26, n)) for lo in range(0, n, 26)]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for lo, hi in chunks:
+            torch.manual_seed(4242 + lo)
+            out = so.run_step(params, views[lo:hi], road[lo:hi], training=False)
+            ref_logits.append(out["logits"])
+            ref_bin.append(out["probs"].round())
+    res["oracle_seconds"] = time.perf_counter() - t0
+    for name, loader in loaders.items():
+        old = loader.graph_max_batch
+        loader.graph_max_batch = 0                        # the CPU-generator dropout patch cannot be graph-captured
+        flips, worst, ts_err, ts_pairs = 0, 0.0, 0.0, []
+        with cpu_rng_dropout(), torch.no_grad():
+            for (lo, hi), rl, rb in zip(chunks, ref_logits, ref_bin):
+                torch.manual_seed(4242 + lo)
+                got = loader.get_binary_road_map(views[lo:hi].to(loader.device)).cpu()
+                diff = got != rb
+                flips += int(diff.sum())
+                if diff.any():
+                    worst = max(worst, float(rl[diff].abs().max()))
+                t = road[lo:hi].float()
+                tp, nt, nr = so.threat_score_counts(t, got)
+                ours = tp / (nt + nr - tp)
+                ref_ts = float(so.threat_score(t, rb))    # the reference's fp32 sums, exact for <= 26 scenes
+                ts_pairs.append([ours, ref_ts])
+                ts_err = max(ts_err, abs(ours - ref_ts))
+        loader.graph_max_batch = old
+        res[name] = {"flipped_ppm": flips / (n * MAP * MAP) * 1e6, "flipped_pixels": flips,
+                     "max_abs_reference_logit_among_flipped": worst, "ts_rounded_max_abs_err_per_chunk": ts_err,
+                     "ts_rounded_ours_vs_reference_first_chunk": ts_pairs[0]}
+    res["min_abs_reference_logit"] = float(min(float(l.abs().min()) for l in ref_logits))
+    res["note"] = ("random-init weights put the logits at ~N(0, 0.06^2), crowded around the threshold: the fp32 path may flip only "
+                   "pixels whose reference logit is within ~1e-6 of it; the bf16 path flips those within bf16 rounding of the activations")
+    return res
+
+
 
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -546,5 +684,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == "inference":
+        run_inference(a)
     else:
         run_ours(a)

@@ -185,6 +185,13 @@ int dd_bce_prob_bwd(const float* probs, const float* target, const float* grad_o
                     long long n, void* stream);
 size_t dd_bce_prob_workspace_bytes(void);
 
+/* ---- 8(f)3: bounding-box evaluation ------------------------------------------------------------------
+ * compute_ats_bounding_boxes (helper.py:33-72, with compute_iou :79-83): boxes1 [n1,2,4], boxes2 [n2,2,4] fp32
+ * (metres; rows x / y; columns fl, fr, bl, br) -> ats f32[1], the IoU-thresholded average threat score.
+ * iou_matrix (optional, may be NULL): f32 [n1,n2], the reference's iou_matrix (0 where the extents do not overlap). */
+int dd_ats_bounding_boxes(const float* boxes1, int n1, const float* boxes2, int n2, float* iou_matrix, float* ats,
+                          void* stream);
+
 /* ---- A14: mean squared error (autoencoder.py:91) ---------------------------------------------*/
 int dd_mse_fwd(const float* y, const float* y_hat, float* loss, void* workspace, size_t ws_bytes,
                long long n, void* stream);

@@ -471,3 +471,87 @@ def init_roadmap_params(hidden: int, latent: int, view_h: int, view_w: int, map_
     p[e + "fc_z_out.weight"], p[e + "fc_z_out.bias"] = uni((latent, hidden), hidden), uni((latent,), hidden)
     p["fc1.weight"], p["fc1.bias"] = uni((map_hw * map_hw, latent), latent), uni((map_hw * map_hw,), latent)
     return p
+
+
+# ----------------------------------------------------------------------------------------
+# 8(f)3: compute_ats_bounding_boxes (helper.py:33-72) with a stand-in for shapely's polygons
+# ----------------------------------------------------------------------------------------
+def _hull(points):
+    """Convex hull (counter-clockwise, no collinear points) of a few 2-D points -- what
+    ``Polygon(torch.t(box)).convex_hull`` (helper.py:80-81) yields for a box's four corners.  shapely (GEOS, unpinned in
+    requirements.txt) is not installable here: this is a pure-Python float64 stand-in, pinned by analytic cases in
+    tests/test_oracle.py rather than by shapely itself."""
+    pts = sorted(set((float(x), float(y)) for x, y in points))
+    if len(pts) < 3:
+        return pts
+
+    def cross(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    lower, upper = [], []
+    for p in pts:
+        while len(lower) >= 2 and cross(lower[-2], lower[-1], p) <= 0:
+            lower.pop()
+        lower.append(p)
+    for p in reversed(pts):
+        while len(upper) >= 2 and cross(upper[-2], upper[-1], p) <= 0:
+            upper.pop()
+        upper.append(p)
+    return lower[:-1] + upper[:-1]
+
+
+def _poly_area(poly):
+    return 0.5 * abs(sum(poly[i][0] * poly[(i + 1) % len(poly)][1] - poly[(i + 1) % len(poly)][0] * poly[i][1]
+                         for i in range(len(poly)))) if len(poly) >= 3 else 0.0
+
+
+def _clip(subject, clip):
+    """Sutherland-Hodgman: the part of convex ``subject`` inside convex counter-clockwise ``clip``."""
+    out = list(subject)
+    for i in range(len(clip)):
+        a, b = clip[i], clip[(i + 1) % len(clip)]
+        side = lambda p: (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])  # noqa: E731
+        inp, out = out, []
+        for k in range(len(inp)):
+            p, q = inp[k], inp[(k + 1) % len(inp)]
+            sp, sq = side(p), side(q)
+            if sp >= 0:
+                out.append(p)
+            if (sp > 0 > sq) or (sp < 0 < sq):
+                t = sp / (sp - sq)
+                out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+        if not out:
+            break
+    return out
+
+
+def compute_iou(box1: torch.Tensor, box2: torch.Tensor) -> float:
+    """helper.py:79-83: intersection area / union area of the two corner sets' convex hulls."""
+    a, b = _hull(torch.t(box1).tolist()), _hull(torch.t(box2).tolist())
+    inter = _poly_area(_clip(a, b)) if len(a) >= 3 and len(b) >= 3 else 0.0
+    return inter / (_poly_area(a) + _poly_area(b) - inter)
+
+
+def compute_ats_bounding_boxes(boxes1: torch.Tensor, boxes2: torch.Tensor):
+    """helper.py:33-72 line by line (torch ops kept: they fix the float32 rounding of the score); returns
+    (average_threat_score 0-dim float32 tensor, iou_matrix)."""
+    num_boxes1, num_boxes2 = boxes1.size(0), boxes2.size(0)
+    b1_max_x, b1_min_x = boxes1[:, 0].max(dim=1)[0], boxes1[:, 0].min(dim=1)[0]
+    b1_max_y, b1_min_y = boxes1[:, 1].max(dim=1)[0], boxes1[:, 1].min(dim=1)[0]
+    b2_max_x, b2_min_x = boxes2[:, 0].max(dim=1)[0], boxes2[:, 0].min(dim=1)[0]
+    b2_max_y, b2_min_y = boxes2[:, 1].max(dim=1)[0], boxes2[:, 1].min(dim=1)[0]
+    cond = ((b1_max_x.unsqueeze(1) > b2_min_x.unsqueeze(0)) * (b1_min_x.unsqueeze(1) < b2_max_x.unsqueeze(0)) *
+            (b1_max_y.unsqueeze(1) > b2_min_y.unsqueeze(0)) * (b1_min_y.unsqueeze(1) < b2_max_y.unsqueeze(0)))
+    iou_matrix = torch.zeros(num_boxes1, num_boxes2)
+    for i in range(num_boxes1):
+        for j in range(num_boxes2):
+            if cond[i][j]:
+                iou_matrix[i][j] = compute_iou(boxes1[i], boxes2[j])
+    iou_max = iou_matrix.max(dim=0)[0]
+    total_threat_score, total_weight = 0, 0
+    for threshold in [0.5, 0.6, 0.7, 0.8, 0.9]:
+        tp = (iou_max > threshold).sum()
+        threat_score = tp * 1.0 / (num_boxes1 + num_boxes2 - tp)
+        total_threat_score += 1.0 / threshold * threat_score
+        total_weight += 1.0 / threshold
+    return total_threat_score / total_weight, iou_matrix

@@ -523,3 +523,33 @@ def test_relu_mask_ragged_tail(dd):
     out = torch.empty_like(g)
     call("dd_relu_mask", g.data_ptr(), a.data_ptr(), out.data_ptr(), 0, 1003, stream_ptr())
     assert torch.equal(out, g * (a > 0))
+
+
+# ------------------------------------------------------------------------------- boxes -------
+@pytest.mark.parametrize("n1,n2,seed", [(7, 9, 0), (20, 20, 1), (1, 5, 2), (33, 3, 3)])
+def test_ats_bounding_boxes_matches_the_reference_loop(dd, n1, n2, seed):
+    """compute_ats_bounding_boxes (helper.py:33-72) on the device against the line-by-line restatement (Python pair loop,
+    float64 polygon stand-in for shapely): IoU matrix to 1e-6, the score bit for bit (integer counts and the reference's
+    float32 arithmetic)."""
+    import math
+    from driving_dirty_b200.utils.helper import compute_ats_bounding_boxes
+    g = torch.Generator().manual_seed(100 + seed)
+
+    def boxes(n, jitter):
+        c = torch.rand(n, 2, generator=g) * 16 - 8
+        ang = torch.rand(n, generator=g) * math.pi
+        out = []
+        for k in range(n):
+            cs, sn = math.cos(float(ang[k])), math.sin(float(ang[k]))
+            pts = [(2.3, 1.0), (2.3, -1.0), (-2.3, 1.0), (-2.3, -1.0)]
+            out.append(torch.tensor([[float(c[k, 0]) + cs * x - sn * y for x, y in pts],
+                                     [float(c[k, 1]) + sn * x + cs * y for x, y in pts]]))
+        return torch.stack(out) + jitter
+    b2 = boxes(n2, 0.0)
+    b1 = torch.cat([b2[: min(n1, n2) // 2] + 0.05 * torch.randn(min(n1, n2) // 2, 2, 4, generator=g),      # near matches
+                    boxes(n1 - min(n1, n2) // 2, 0.0)])
+    ref, ref_iou = so.compute_ats_bounding_boxes(b1, b2)
+    got, iou = compute_ats_bounding_boxes(b1.cuda(), b2.cuda(), return_iou=True)
+    assert float((iou.cpu() - ref_iou).abs().max()) < 1e-6
+    assert float(got) == float(ref)
+    assert float(compute_ats_bounding_boxes(b2.cuda(), b2.cuda())) == 1.0

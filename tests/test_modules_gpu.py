@@ -198,7 +198,7 @@ def test_full_size_train_bf16(golden):
 def test_model_loader_binary_road_map(golden):
     from driving_dirty_b200.model_loader import ModelLoader
     g, model, params, views, road = _load_case(golden, "roadmap_small")
-    loader = ModelLoader(model)
+    loader = ModelLoader(model, graph_max_batch=0)      # the CPU-RNG dropout patch cannot be captured into a CUDA graph
     with cpu_rng_dropout():
         torch.manual_seed(g["seed_fwd"])
         rm = loader.get_binary_road_map(views.cuda())
@@ -227,7 +227,7 @@ def test_raw_byte_front_end_on_the_model_path(golden, dtype):
     gen = torch.Generator().manual_seed(99)
     raw = torch.randint(0, 256, views.shape, dtype=torch.uint8, generator=gen)
     as_float = raw.float() / 255
-    loader = ModelLoader(model)
+    loader = ModelLoader(model, graph_max_batch=0)      # the CPU-RNG dropout patch cannot be captured into a CUDA graph
     outs = []
     with cpu_rng_dropout():
         for src in (as_float.cuda(), raw.cuda(), raw, raw):          # device fp32, device bytes, host bytes (twice: buffer reuse)
@@ -451,3 +451,52 @@ def test_unpatched_dropout_shares_the_philox_stream():
             assert rel_max_err(got, grads[name]) < tol, name
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_run_test_driver_scores_match_per_scene_oracle(golden, tmp_path):
+    """The README's evaluation entry point (utils/run_test.py): scores over a saved scene file equal the oracle's per-scene
+    threat score of the binarised reference forward, averaged, and the harness' box score of the placeholder boxes."""
+    from driving_dirty_b200.model_loader import ModelLoader
+    from driving_dirty_b200.utils import run_test
+    g, model, params, views, road = _load_case(golden, "roadmap_small")
+    boxes = so.synthetic_boxes(g["batch"])
+    loader = ModelLoader(model, graph_max_batch=0)      # the CPU-RNG dropout patch cannot be captured into a CUDA graph
+    with cpu_rng_dropout():
+        torch.manual_seed(11)
+        res = run_test.evaluate(loader, views, road, boxes, batch_size=g["batch"])
+        torch.manual_seed(11)
+        with torch.no_grad():
+            ref = so.run_step(params, views, road, training=False)
+    per_scene = [float(so.threat_score(road[i].float(), ref["probs"][i].round())) for i in range(g["batch"])]
+    assert abs(res["road_map_ts"] - sum(per_scene) / len(per_scene)) < 1e-5
+    placeholder = loader.get_bounding_boxes(views.cuda())
+    want = sum(float(so.compute_ats_bounding_boxes(placeholder[i].cpu(), boxes[i])[0]) for i in range(g["batch"])) / g["batch"]
+    assert abs(res["bounding_box_ats"] - want) < 1e-6 and res["scenes"] == g["batch"]
+
+
+def test_model_loader_cuda_graph_path_equals_eager(golden):
+    """Batches up to ``graph_max_batch`` replay a captured CUDA graph: same bits as the eager forward for the same seed
+    (the torch dropout inside the graph draws from the generator's Philox offset like the eager call), fresh masks per call."""
+    from driving_dirty_b200.model_loader import ModelLoader
+    g, model, params, views, road = _load_case(golden, "roadmap_small", "bf16")
+    eager, graphed = ModelLoader(model, graph_max_batch=0), ModelLoader(model, graph_max_batch=8)
+    v = views.cuda()
+    outs = []
+    for loader in (eager, graphed, graphed, eager):
+        torch.manual_seed(77)
+        outs.append(loader.get_binary_road_map(v))
+    assert len(graphed._graphs) == 1
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    torch.manual_seed(78)
+    other = graphed.get_binary_road_map(v)
+    assert not torch.equal(other, outs[0])            # another seed, another dropout mask (SURVEY D5)
+    torch.manual_seed(78)
+    assert torch.equal(eager.get_binary_road_map(v), other)
+    # a second shape gets its own graph; raw bytes go through the same path
+    raw = (v[:2] * 255).round().to(torch.uint8)
+    torch.manual_seed(5)
+    a = graphed.get_binary_road_map(raw)
+    torch.manual_seed(5)
+    b = eager.get_binary_road_map(raw)
+    assert torch.equal(a, b) and len(graphed._graphs) == 2

@@ -146,3 +146,29 @@ def test_bb_full_b1(golden):
     out["loss"].backward()
     for k in g["grad_norm"]:
         assert torch.equal(so.strided_sample(q[k].grad, 512), g["grad_sample"][k]), k
+
+
+def test_box_iou_stand_in_on_analytic_cases():
+    """The shapely stand-in of compute_iou (helper.py:79-83) against cases with a closed form; corners in the dataset's
+    order fl, fr, bl, br (a bow-tie as a ring, hence the reference's convex_hull)."""
+    def box(cx, cy, dx, dy, ang=0.0):
+        import math
+        c, s = math.cos(ang), math.sin(ang)
+        pts = [(dx, dy), (dx, -dy), (-dx, dy), (-dx, -dy)]
+        xs = [cx + c * x - s * y for x, y in pts]
+        ys = [cy + s * x + c * y for x, y in pts]
+        return torch.tensor([xs, ys], dtype=torch.float32)
+    a = box(0, 0, 2, 1)
+    assert abs(so.compute_iou(a, a) - 1.0) < 1e-12
+    assert abs(so.compute_iou(a, box(2, 0, 2, 1)) - (4.0 / 12.0)) < 1e-6          # half overlap: 4 / (8 + 8 - 4)
+    assert abs(so.compute_iou(a, box(1, 1, 2, 1)) - (3.0 / 13.0)) < 1e-6
+    assert so.compute_iou(a, box(10, 0, 2, 1)) == 0.0
+    sq, diamond = box(0, 0, 1, 1), box(0, 0, 1, 1, ang=0.7853981633974483)        # unit square vs the same rotated 45 deg
+    inter = 8 * (2 ** 0.5 - 1)                                                    # regular octagon of inradius 1
+    assert abs(so.compute_iou(sq, diamond) - inter / (8 - inter)) < 1e-6
+    # score: identical sets -> every box matches at every threshold -> tp = n, ts = n / (2n - n) = 1
+    boxes = torch.stack([box(3 * i, 0, 1, 1) for i in range(4)])
+    ats, iou = so.compute_ats_bounding_boxes(boxes, boxes)
+    assert abs(float(ats) - 1.0) < 1e-6 and torch.allclose(torch.diagonal(iou), torch.ones(4))
+    ats0, _ = so.compute_ats_bounding_boxes(boxes, boxes + 100.0)
+    assert float(ats0) == 0.0
