@@ -442,16 +442,17 @@ def run_inference(args):
                 continue                                  # the fp32 SIMT parity path is not the throughput path
             iters = max(3, min(args.steps * 4, 256 // b))
             row = {"dtype": name, "batch": b}
+            out_h = torch.empty(b, MAP, MAP, dtype=torch.uint8).pin_memory()
             for mode, src in (("resident", views_d[:b]), ("e2e", views_h[:b])):
                 for _ in range(3):
-                    out = loader.get_binary_road_map(src)
+                    out = loader.get_binary_road_map(src, as_bytes=(mode == "e2e"))
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(iters):
-                    out = loader.get_binary_road_map(src)
+                    out = loader.get_binary_road_map(src, as_bytes=(mode == "e2e"))
                     if mode == "e2e":
-                        out_h = out.to("cpu")              # binary maps back on the host, every call
+                        out_h.copy_(out, non_blocking=False)   # the binary maps (bytes) back on the host, every call
                 e1.record()
                 torch.cuda.synchronize()
                 sec = e0.elapsed_time(e1) * 1e-3 / iters
@@ -478,8 +479,8 @@ def run_inference(args):
                        "batch_per_gpu": best["batch"], "parallelism": f"replicas x{world}",
                        "l2": "activations of the best batch exceed the 126 MB L2; small batches are L2 resident by nature"},
             "e2e": {"value": float(t[1]), "unit": UNIT, "h2d_bytes_per_step": best["batch"] * 6 * 3 * VIEW_H * VIEW_W,
-                    "d2h_bytes_per_step": best["batch"] * MAP * MAP * 4,
-                    "note": "pinned host bytes staged by ModelLoader every call, float32 binary maps copied back to the host"},
+                    "d2h_bytes_per_step": best["batch"] * MAP * MAP,
+                    "note": "pinned host camera bytes copied in by ModelLoader every call, the uint8 binary maps copied back to pinned host memory"},
             "gpu_launches": int(launches), "clocks": clocks, "sweep": sweep,
             "conv_stack": {"tflops_at_best_batch": FLOP_CONVS_PER_SCENE * best["resident_scenes_s"] / 1e12,
                            "frac_of_bf16_peak": FLOP_CONVS_PER_SCENE * best["resident_scenes_s"] / 1e12 / pk["bf16_tflops"],

@@ -65,6 +65,8 @@ class ModelLoader:
         copy on a side stream (a pageable source would make the copy synchronous and staged by the driver)."""
         if samples.is_cuda:
             return samples.to(self.device)
+        if samples.is_pinned():                                  # already page-locked: one asynchronous copy, no staging
+            return samples.to(self.device, non_blocking=True)
         key = (tuple(samples.shape), samples.dtype)
         slot = self._staging.get(key)
         if slot is None:
@@ -85,19 +87,18 @@ class ModelLoader:
         return dev
 
     @torch.no_grad()
-    def get_binary_road_map(self, samples):
+    def get_binary_road_map(self, samples, as_bytes=False):
         """samples: tensor [B,6,3,256,306], fp32 in [0,1] (the competition's CUDA tensor) or uint8 raw camera bytes, on the
         device or on the host (then staged through pinned memory) -> CUDA float tensor [B,800,800] of 0./1., equal to
-        ``sigmoid(logits).round()`` of the reference forward (on ``bytes.float() / 255`` for raw bytes)."""
+        ``sigmoid(logits).round()`` of the reference forward (on ``bytes.float() / 255`` for raw bytes).
+        ``as_bytes``: the same map as uint8 (what the kernel writes: a quarter of the bytes to store or copy back)."""
         x = self.stage(samples)
-        if 0 < x.shape[0] <= self.graph_max_batch:
-            return self._replay(x)
-        return self._forward(x)
+        binary = self._replay(x) if 0 < x.shape[0] <= self.graph_max_batch else self._forward(x)
+        return binary if as_bytes else binary.float()
 
     def _forward(self, x):
         logits = self.model._logits(x)
-        _, binary = ops.sigmoid_binary(logits)
-        return binary.float()
+        return ops.binary_map(logits)
 
     def _replay(self, x):
         """CUDA-graph path: the whole forward (ToTensor pass, convs, pool, dense blocks with their torch dropout -- the

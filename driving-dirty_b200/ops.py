@@ -384,6 +384,21 @@ def sigmoid_binary(logits):
     return _SigmoidBinary.apply(logits)
 
 
+def binary_map(logits: torch.Tensor) -> torch.Tensor:
+    """``sigmoid(logits).round()`` (roadmap_bce_v2.py:81,140) as a uint8 map, without materialising the probabilities:
+    the inference front-end's last pass reads the logits once and writes one byte per pixel."""
+    _require_cuda(logits)
+    logits = _c(logits)
+    dev = logits.device
+    binary = torch.empty(logits.shape, dtype=torch.uint8, device=dev)
+    stats = torch.empty(4, dtype=torch.float32, device=dev)
+    counts = torch.empty(4, dtype=torch.int64, device=dev)
+    ws, wn = _bce_ws(dev)
+    call("dd_bce_ts_fwd", logits.data_ptr(), None, 0, None, binary.data_ptr(), stats.data_ptr(), counts.data_ptr(),
+         ws.data_ptr(), wn, logits.numel(), stream_ptr())
+    return binary
+
+
 def threat_score(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """compute_ts_road_map (helper.py:74-77) for two maps of any float values -> 0-dim tensor."""
     _require_cuda(a, b)
