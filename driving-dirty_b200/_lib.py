@@ -53,6 +53,7 @@ SIGNATURES = {
     "dd_conv2d_dgrad": (_I, [_P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "dd_conv2d_wgrad": (_I, [_P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "dd_conv2d_workspace_bytes": (_Z, [_P]),
+    "dd_conv2d_tc_supported": (_I, [_P, _I, _I]),
     "dd_view_extract": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "dd_nhwc_place": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "dd_sigmoid_bwd": (_I, [_P, _P, _P, _I, _L, _P]),

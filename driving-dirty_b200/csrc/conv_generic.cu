@@ -305,6 +305,25 @@ int launch_wgrad(const T* P, const T* Q, float* partial, const WGeo& g, int taps
 }
 }  // namespace
 
+// tcgen05 path for the wide stride-1 (dilated) layers: conv_dil_tc.cu
+namespace dd {
+bool conv_dil_tc_supported(int K, int N, int KT, int D);
+size_t conv_dil_tc_pack_bytes(int K, int N, int KT);
+int conv_dil_tc(const void* in, const float* w, long long sn, long long sk, int flip, const float* bias, const void* mask, void* out,
+                void* pack_ws, int B, int Hi, int Wi, int Ho, int Wo, int K, int N, int KT, int D, int sign, int off, int relu,
+                cudaStream_t st);
+}  // namespace dd
+
+// pass: 0 forward, 1 input gradient.  bf16, stride 1, square filter of 3 or 7 taps, one dilation and padding for both axes.
+static bool tc_ok(const dd_conv_desc* d, int dtype, int pass, int act) {
+  if (dtype != DD_BF16 || d->sh != 1 || d->sw != 1 || d->kh != d->kw || d->dh != d->dw || d->ph != d->pw) return false;
+  if (pass == 0 && act == 2) return false;
+  const int K = pass == 0 ? d->Cin : d->Cout, N = pass == 0 ? d->Cout : d->Cin;
+  return dd::conv_dil_tc_supported(K, N, d->kh, d->dh);
+}
+
+extern "C" int dd_conv2d_tc_supported(const dd_conv_desc* d, int dtype, int pass) { return d && desc_ok(d) && tc_ok(d, dtype, pass, 0); }
+
 extern "C" size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d) {
   if (!desc_ok(d)) return 256;
   const long long np_out = (long long)d->B * d->Ho * d->Wo, np_in = (long long)d->B * d->Hi * d->Wi;
@@ -324,6 +343,15 @@ extern "C" int dd_conv2d_fwd(const void* x, const float* w, const float* bias, v
   DD_REQUIRE(act >= 0 && act <= 2, DD_ERR_BAD_ARG, "dd_conv2d_fwd: act %d", act);
   cudaStream_t st = dd::as_stream(stream);
   const int taps = d->kh * d->kw;
+  if (tc_ok(d, dtype, 0, act)) {
+    // ConvTranspose2d [Cin][Cout][kh][kw]: gathers from h - D*kh + p;  Conv2d [Cout][Cin][kh][kw]: from h + D*kh - p
+    const long long T = taps;
+    if (d->transposed)
+      return dd::conv_dil_tc(x, w, T, (long long)d->Cout * T, 0, bias, nullptr, y, workspace, d->B, d->Hi, d->Wi, d->Ho, d->Wo, d->Cin,
+                             d->Cout, d->kh, d->dh, -1, d->ph, act == 1, st);
+    return dd::conv_dil_tc(x, w, (long long)d->Cin * T, T, 1, bias, nullptr, y, workspace, d->B, d->Hi, d->Wi, d->Ho, d->Wo, d->Cin,
+                           d->Cout, d->kh, d->dh, +1, -d->ph, act == 1, st);
+  }
   float* wg = (float*)workspace;
   // conv weights are [Cout][Cin][t] (need wg[t][ci][co] = w[co][ci][t]: swap); convT weights are [Cin][Cout][t]
   wprep_kernel<<<64, 256, 0, st>>>(w, wg, d->Cin, d->Cout, taps, d->transposed ? 0 : 1);
@@ -343,6 +371,15 @@ extern "C" int dd_conv2d_dgrad(const void* dy, const float* w, const void* x_mas
   DD_REQUIRE(ws_bytes >= wg_bytes(d), DD_ERR_WORKSPACE, "dd_conv2d_dgrad: workspace %zu < %zu", ws_bytes, wg_bytes(d));
   cudaStream_t st = dd::as_stream(stream);
   const int taps = d->kh * d->kw;
+  if (tc_ok(d, dtype, 1, 0)) {
+    // gathered tensor = dy (Cout channels), produced = dx (Cin channels)
+    const long long T = taps;
+    if (d->transposed)
+      return dd::conv_dil_tc(dy, w, (long long)d->Cout * T, T, 1, nullptr, x_mask, dx, workspace, d->B, d->Ho, d->Wo, d->Hi, d->Wi,
+                             d->Cout, d->Cin, d->kh, d->dh, +1, -d->ph, 0, st);
+    return dd::conv_dil_tc(dy, w, T, (long long)d->Cin * T, 0, nullptr, x_mask, dx, workspace, d->B, d->Ho, d->Wo, d->Hi, d->Wi, d->Cout,
+                           d->Cin, d->kh, d->dh, -1, d->ph, 0, st);
+  }
   float* wg = (float*)workspace;
   // gathered tensor = dy (Cout channels), produced = dx (Cin channels): wg[t][co][ci]
   wprep_kernel<<<64, 256, 0, st>>>(w, wg, d->Cout, d->Cin, taps, d->transposed ? 1 : 0);

@@ -164,6 +164,11 @@ int dd_conv2d_dgrad(const void* dy, const float* w, const void* x_mask, void* dx
 int dd_conv2d_wgrad(const void* x, const void* dy, float* dw, float* db, const dd_conv_desc* d,
                     int dtype, void* workspace, size_t ws_bytes, void* stream);
 size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d);
+/* 1 when pass (0 forward, 1 input gradient) of this layer runs on the tcgen05 implicit-GEMM kernel (csrc/conv_dil_tc.cu):
+ * bf16, stride 1, square filter of 3 or 7 taps with one dilation / padding for both axes, (gathered, produced) channels in
+ * {(96,64), (64,32), (32,16), (32,32), (64,96), (32,64)} -- the merging CNN's up_conv_1..3, rm_conv_2, out_conv and the
+ * decoder's dc1 / dc2.  Everything else (and fp32: the parity path) runs on the CUDA-core engine. */
+int dd_conv2d_tc_supported(const dd_conv_desc* d, int dtype, int pass);
 
 /* ---- A15-A17: data movement and loss of the bounding-box model ------------------------------------
  * dd_view_extract: one camera of every scene as an NHWC image [B,H',W',3] with the rot90 / flip of

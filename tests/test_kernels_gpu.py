@@ -497,6 +497,10 @@ def test_conv2d_generic_fwd_dgrad_wgrad(dd, layer, dtype, tol, relu):
     g = torch.Generator().manual_seed(sum(map(ord, layer)))
     mod_cls = torch.nn.ConvTranspose2d if L["t"] else torch.nn.Conv2d
     mod = mod_cls(L["cin"], L["cout"], kernel_size=L["k"], stride=L["s"], padding=L["p"], dilation=L["d"])
+    with torch.no_grad():
+        # bf16 path: the tensor-core layers read their weights as bf16 operands; give the reference the same operands, or
+        # outputs within rounding of zero flip their ReLU mask and the comparison measures the flips, not the kernel
+        mod.weight.copy_(q(mod.weight, dtype))
     x = q(torch.randn(B, L["cin"], *L["hw"], generator=g), dtype).requires_grad_(True)
     y = mod(x)
     if relu:
@@ -514,6 +518,62 @@ def test_conv2d_generic_fwd_dgrad_wgrad(dd, layer, dtype, tol, relu):
     assert rel_max_err(to_nchw(xd.grad), x.grad) < tol
     assert rel_max_err(m2.weight.grad, mod.weight.grad) < tol
     assert rel_max_err(m2.bias.grad, mod.bias.grad) < tol
+
+
+TC_LAYERS = {
+    # name: (transposed, cin, cout, k, pad, dil, (H, W), batch) -- every (gathered, produced) channel pair the tcgen05
+    # implicit-GEMM kernel is instantiated for, at sizes with several column strips, row groups and residue classes
+    "up_conv1_96_64_k7d7": (True, 96, 64, 7, 0, 7, (20, 150), 2),
+    "up_conv2_64_32_k7d7": (True, 64, 32, 7, 0, 7, (30, 140), 2),
+    "up_conv3_32_16_k7d7": (True, 32, 16, 7, 0, 7, (33, 100), 1),
+    "dc1_64_32_k3p1": (True, 64, 32, 3, 1, 1, (40, 153), 2),
+    "dc2_32_32_k3p1": (True, 32, 32, 3, 1, 1, (128, 153), 1),
+    "out_conv_32_32_k3": (False, 32, 32, 3, 0, 1, (50, 258), 2),
+    "rm_conv2_32_32_k3d3": (False, 32, 32, 3, 0, 3, (41, 262), 1),
+}
+
+
+@pytest.mark.parametrize("layer", sorted(TC_LAYERS))
+def test_conv2d_tcgen05_layers(dd, layer):
+    """The tcgen05 implicit-GEMM path of dd_conv2d_fwd / dd_conv2d_dgrad (csrc/conv_dil_tc.cu: residue-class row groups, taps
+    scattered over N, weight slabs streamed by TMA) against torch's CPU conv2d / conv_transpose2d and autograd on the same
+    bf16-rounded operands: forward with bias + ReLU, input gradient with the ReLU mask of the layer input."""
+    import ctypes
+    from driving_dirty_b200 import _lib
+    t, cin, cout, k, p, d, hw, B = TC_LAYERS[layer]
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(sum(map(ord, layer)))
+    mod_cls = torch.nn.ConvTranspose2d if t else torch.nn.Conv2d
+    mod = mod_cls(cin, cout, kernel_size=k, stride=1, padding=p, dilation=d)
+    with torch.no_grad():
+        mod.weight.copy_(q(mod.weight, dtype))            # the kernel reads the weights as bf16 operands
+    x = q(F.relu(torch.randn(B, cin, *hw, generator=g)), dtype).requires_grad_(True)
+    y = F.relu(mod(x))
+    dy = q(torch.randn(y.shape, generator=g), dtype)
+    y.backward(dy)
+    m2 = mod_cls(cin, cout, kernel_size=k, stride=1, padding=p, dilation=d).cuda()
+    m2.load_state_dict(mod.state_dict())
+    desc = _lib.ConvDesc(B, cin, cout, hw[0], hw[1], y.shape[2], y.shape[3], k, k, 1, 1, p, p, d, d, int(t))
+    assert _lib.load().dd_conv2d_tc_supported(ctypes.byref(desc), 1, 0) == 1
+    # the input gradient gathers the layer's OUTPUT channels: 16 of them (up_conv_3) are below the kernel's 32-channel K chunk
+    assert _lib.load().dd_conv2d_tc_supported(ctypes.byref(desc), 1, 1) == int(cout % 32 == 0)
+    assert _lib.load().dd_conv2d_tc_supported(ctypes.byref(desc), 0, 0) == 0          # fp32 stays on the CUDA-core parity engine
+    xd = nhwc(x.detach(), dtype).requires_grad_(True)
+    yd = dd.conv2d_nhwc(xd, m2, relu=True)
+    assert tuple(yd.shape) == (B, y.shape[2], y.shape[3], cout)
+    assert rel_max_err(to_nchw(yd.detach()), y) < 1e-2
+    yd.backward(nhwc(dy, dtype))
+    assert rel_max_err(to_nchw(xd.grad), x.grad) < 1e-2
+    assert rel_max_err(m2.weight.grad, mod.weight.grad) < 1e-2
+    # the ReLU mask of the layer input, fused into the input-gradient epilogue (dd_conv2d_dgrad's x_mask)
+    st, code = _lib.stream_ptr(), 1
+    n = int(_lib.load().dd_conv2d_workspace_bytes(ctypes.byref(desc)))
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dym = (nhwc(dy, dtype).float() * (yd.detach().float() > 0)).to(dtype)
+    dxm = torch.empty_like(xd)
+    _lib.call("dd_conv2d_dgrad", dym.data_ptr(), m2.weight.detach().float().contiguous().data_ptr(), xd.detach().data_ptr(),
+              dxm.data_ptr(), ctypes.byref(desc), code, ws.data_ptr(), n, st)
+    assert rel_max_err(to_nchw(dxm), x.grad * (x.detach() > 0)) < 1e-2
 
 
 def test_relu_mask_ragged_tail(dd):
