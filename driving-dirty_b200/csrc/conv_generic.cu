@@ -312,7 +312,16 @@ size_t conv_dil_tc_pack_bytes(int K, int N, int KT);
 int conv_dil_tc(const void* in, const float* w, long long sn, long long sk, int flip, const float* bias, const void* mask, void* out,
                 void* pack_ws, int B, int Hi, int Wi, int Ho, int Wo, int K, int N, int KT, int D, int sign, int off, int relu,
                 cudaStream_t st);
+bool conv_dil_wgrad_tc_supported(int K, int N, int KT, int D);
+size_t conv_dil_wgrad_tc_ws_bytes(int K, int N, int KT);
+int conv_dil_wgrad_tc(const void* in, const void* dout, float* dw, long long sn, long long sk, void* ws, size_t ws_bytes, int B,
+                      int Hi, int Wi, int Ho, int Wo, int K, int N, int KT, int D, int sign, int off, cudaStream_t st);
 }  // namespace dd
+
+static bool tc_wgrad_ok(const dd_conv_desc* d, int dtype) {
+  if (dtype != DD_BF16 || d->sh != 1 || d->sw != 1 || d->kh != d->kw || d->dh != d->dw || d->ph != d->pw) return false;
+  return dd::conv_dil_wgrad_tc_supported(d->Cin, d->Cout, d->kh, d->dh);
+}
 
 // pass: 0 forward, 1 input gradient.  bf16, stride 1, square filter of 3 or 7 taps, one dilation and padding for both axes.
 static bool tc_ok(const dd_conv_desc* d, int dtype, int pass, int act) {
@@ -322,7 +331,10 @@ static bool tc_ok(const dd_conv_desc* d, int dtype, int pass, int act) {
   return dd::conv_dil_tc_supported(K, N, d->kh, d->dh);
 }
 
-extern "C" int dd_conv2d_tc_supported(const dd_conv_desc* d, int dtype, int pass) { return d && desc_ok(d) && tc_ok(d, dtype, pass, 0); }
+extern "C" int dd_conv2d_tc_supported(const dd_conv_desc* d, int dtype, int pass) {
+  if (!d || !desc_ok(d)) return 0;
+  return pass == 2 ? tc_wgrad_ok(d, dtype) : tc_ok(d, dtype, pass, 0);
+}
 
 extern "C" size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d) {
   if (!desc_ok(d)) return 256;
@@ -331,7 +343,9 @@ extern "C" size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d) {
   const size_t partial = (size_t)wgrad_splits(d, pivot) * d->kh * d->kw * d->Cin * d->Cout * sizeof(float);
   const size_t chan = (size_t)kChanBlocks * d->Cout * sizeof(double) + 8;
   const size_t a = wg_bytes(d), b = partial + chan;
-  return (a > b ? a : b) + 256;
+  const size_t c = tc_wgrad_ok(d, DD_BF16) ? dd::conv_dil_wgrad_tc_ws_bytes(d->Cin, d->Cout, d->kh) + chan : 0;
+  const size_t m = a > b ? a : b;
+  return (m > c ? m : c) + 256;
 }
 
 extern "C" int dd_conv2d_fwd(const void* x, const float* w, const float* bias, void* y, const dd_conv_desc* d, int dtype,
@@ -403,6 +417,28 @@ extern "C" int dd_conv2d_wgrad(const void* x, const void* dy, float* dw, float* 
   const int taps = d->kh * d->kw;
   const long long np_out = (long long)d->B * d->Ho * d->Wo, np_in = (long long)d->B * d->Hi * d->Wi;
   const long long pivot = d->transposed ? np_in : np_out;
+  if (tc_wgrad_ok(d, dtype)) {
+    // tensor-core path (csrc/conv_dil_wgrad_tc.cu): partials first, then the bias gradient's channel sums
+    const long long T = taps;
+    const size_t tcb = dd::conv_dil_wgrad_tc_ws_bytes(d->Cin, d->Cout, d->kh);
+    int e = d->transposed
+                ? dd::conv_dil_wgrad_tc(x, dy, dw, T, (long long)d->Cout * T, workspace, tcb, d->B, d->Hi, d->Wi, d->Ho, d->Wo, d->Cin,
+                                        d->Cout, d->kh, d->dh, -1, d->ph, st)
+                : dd::conv_dil_wgrad_tc(x, dy, dw, (long long)d->Cin * T, T, workspace, tcb, d->B, d->Hi, d->Wi, d->Ho, d->Wo, d->Cin,
+                                        d->Cout, d->kh, d->dh, +1, -d->ph, st);
+    if (e) return e;
+    if (db) {
+      double* cpart = reinterpret_cast<double*>(((uintptr_t)((uint8_t*)workspace + tcb) + 7) & ~(uintptr_t)7);
+      const int lanes = 256 / d->Cout > 0 ? 256 / d->Cout : 1;
+      const long long want = (np_out + lanes - 1) / lanes;
+      const int nblk = (int)(want < kChanBlocks ? want : kChanBlocks);
+      chansum_kernel<__nv_bfloat16><<<nblk, 256, 0, st>>>((const __nv_bfloat16*)dy, np_out, d->Cout, cpart);
+      if (int e3 = dd::check_launch("conv2d_chansum")) return e3;
+      chansum_fold_kernel<<<(d->Cout + 255) / 256, 256, 0, st>>>(cpart, nblk, d->Cout, db);
+      return dd::check_launch("conv2d_chansum_fold");
+    }
+    return 0;
+  }
   const int splits = wgrad_splits(d, pivot);
   WGeo g;
   g.B = d->B;
