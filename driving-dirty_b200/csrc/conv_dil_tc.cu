@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) conv_dil_tc_kernel(const __grid
       }
       umma::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&bars->acc_empty[buf]);
+      if (lane == 0) umma::mbar_arrive_relaxed(&bars->acc_empty[buf]);   // relaxed: a release arrive would first drain this warp's outstanding global stores
       ++ic;
     }
   }

@@ -21,7 +21,6 @@
 // ReLU-mask -> bf16 -> global).  mbarrier rings: slab full/empty (8 deep), accumulator
 // full/empty (4 x 32 TMEM columns), so loads, MMAs and epilogues of different rows overlap.
 #include "dd_common.cuh"
-#include <stdlib.h>
 
 #include "tma_host.h"
 #include "umma.cuh"
@@ -39,14 +38,6 @@ constexpr int W_BYTES = 9 * 4 * 512;  // bf16 weights [tap][cg][co][8 ci]
 constexpr int NPROD = 4;             // producer warps (0..3); warp 4 issues MMAs; warps 5..8 run the epilogue
 constexpr int MMA_WARP = NPROD;
 constexpr int NTHREADS = 32 * (NPROD + 1 + 4);
-
-template <int STRIDE>
-struct Geo {
-  static constexpr int NPIX = (TILE_M - 1) * STRIDE + 3;      // input pixels per slab: 130 / 257
-  static constexpr int PLANES = 4 * STRIDE;                   // stride 2: even + odd pixel planes
-  static constexpr int SLAB_BYTES = PLANES * PS;
-  static constexpr int SMEM = W_BYTES + RING * SLAB_BYTES + 1024;
-};
 
 // Epilogue-side wait: back off between polls so the spinning warps do not take issue slots from the
 // producer / MMA warps that share their schedulers.
@@ -71,50 +62,37 @@ __device__ __forceinline__ void store_pixel32(__nv_bfloat16* dst, const float (&
   umma::stg256(dst + 16, pk + 8);
 }
 
-// One input row -> slab planes, by NT cooperating threads.  Thread (cg = ptid & 3, lp = ptid >> 2)
-// copies pixels lp, lp+NT/4, ...: source and destination advance by constants, only the bounds
-// predicate varies.  PPL > 0: stride-2 layout, odd pixels live PPL planes after the even ones.
-template <int NPIX, int PPL, int PLANE_STRIDE = PS, int NT = 128>
-__device__ __forceinline__ void load_slab(uint32_t dst0, const __nv_bfloat16* __restrict__ rowp, bool row_ok, int c0,
-                                          int W, int ptid) {
-  constexpr bool PARITY_PLANES = PPL > 0;
-  constexpr int PX = NT / 4;          // pixels covered per step
-  const int cg = ptid & 3, lp = ptid >> 2;
-  uint32_t dst = PARITY_PLANES ? dst0 + ((lp & 1) * PPL + cg) * PLANE_STRIDE + (lp >> 1) * 16
-                               : dst0 + cg * PLANE_STRIDE + lp * 16;
-  const __nv_bfloat16* src = rowp + (ptrdiff_t)(c0 + lp) * C + cg * 8;
-  int col = c0 + lp;
-#pragma unroll
-  for (int k = 0; k < (NPIX + PX - 1) / PX; ++k) {
-    if ((k + 1) * PX <= NPIX || lp + k * PX < NPIX) {
-      const bool ok = row_ok && col >= 0 && col < W;
-      umma::cp_async16(dst, ok ? src : rowp, ok ? 16u : 0u);
-    }
-    dst += PARITY_PLANES ? PX * 8 : PX * 16;
-    src += PX * C;
-    col += PX;
-  }
-}
-
 struct Bars {
   uint64_t full[RING], empty[RING], acc_full[NACC], acc_empty[NACC];
   uint32_t tmem_base;
 };
 
-// MODE 0: forward (bias + ReLU).  MODE 1: stride-1 input gradient (flipped/transposed filter,
-// epilogue multiplies by mask > 0).
-template <int STRIDE, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_bfloat16* __restrict__ in,
-                                                                      const float* __restrict__ w_oihw,
-                                                                      const float* __restrict__ bias,
-                                                                      const __nv_bfloat16* __restrict__ mask,
-                                                                      __nv_bfloat16* __restrict__ out, int B, int H,
-                                                                      int W, int Ho, int Wo, int dbg) {
-  using G = Geo<STRIDE>;
+// ================================================================================================
+// Stride-2 32->32 3x3 conv (c3 forward, components.py:21,43), "row marching" gather form: 18 tcgen05.mma (M = 128 output
+// pixels, N = 32, K = 16) per output row into a 32-column TMEM accumulator; every input row is loaded once per strip and
+// used by the three output rows it feeds.  The input row lands as two whole-pixel planes through TMA boxes with an
+// ELEMENT STRIDE of 2 along w (64-byte-swizzled K-major operand layout, profiles/r2_tma_layout_probe.txt): plane 0 =
+// pixels c0, c0+2, ... (129 of them: taps kw = 0 and, one pixel on, kw = 2), plane 1 = pixels c0+1, c0+3, ... (kw = 1), so
+// consecutive output pixels read consecutive 64-byte rows.  Rows / columns outside the image are zero-filled by the TMA
+// unit (= the padding).  Round 1 fed this kernel with cp.async (16-byte pieces, four producer warps): 53 % of the HBM roof.
+// Warps: 0 = TMA producer (one thread), 4 = MMA issuer, 5..8 = epilogue.
+// ================================================================================================
+constexpr int S2_P0 = 17 * 512;                 // plane 0: 129 pixels of 64 B, rounded up to the 512-byte swizzle period
+constexpr int S2_P1 = TILE_M * 64;              // plane 1: 128 pixels
+constexpr int S2_SLAB = S2_P0 + S2_P1;
+constexpr int S2_SLAB_TX = (129 + 128) * 64;
+constexpr int S2_SMEM = W_BYTES + RING * S2_SLAB + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_s2_tc_kernel(const __grid_constant__ CUtensorMap map_in2,
+                                                                        const __grid_constant__ CUtensorMap map_in1,
+                                                                        const float* __restrict__ w_oihw,
+                                                                        const float* __restrict__ bias,
+                                                                        __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                                                        int Ho, int Wo) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_slab = smem + W_BYTES;
-  Bars* bars = reinterpret_cast<Bars*>(smem + W_BYTES + RING * G::SLAB_BYTES);
+  Bars* bars = reinterpret_cast<Bars*>(smem + W_BYTES + RING * S2_SLAB);
   __shared__ float s_bias[C];
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -123,17 +101,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
   const int hsegs = (Ho + ROWS - 1) / ROWS;
   const int items = B * wtiles * hsegs;
 
-  // ---- one-time setup: weights -> bf16 UMMA layout, barriers, TMEM ---------------------------
+  // ---- one-time setup: weights -> bf16 UMMA layout [tap][cg][co][8 ci], barriers, TMEM ----------
   for (int i = tid; i < 9 * C * C; i += NTHREADS) {
-    const int ci = i & 31, co = (i >> 5) & 31, tap = i >> 10;     // (in-channel role, out-channel role)
-    float v;
-    if (MODE == 0) v = w_oihw[(co * C + ci) * 9 + tap];
-    else v = w_oihw[(ci * C + co) * 9 + (8 - tap)];               // dgrad: W[co=in][ci=out][flipped tap]
-    *reinterpret_cast<__nv_bfloat16*>(s_w + (tap * 4 + (ci >> 3)) * 512 + co * 16 + (ci & 7) * 2) = __float2bfloat16_rn(v);
+    const int ci = i & 31, co = (i >> 5) & 31, tap = i >> 10;
+    *reinterpret_cast<__nv_bfloat16*>(s_w + (tap * 4 + (ci >> 3)) * 512 + co * 16 + (ci & 7) * 2) =
+        __float2bfloat16_rn(w_oihw[(co * C + ci) * 9 + tap]);
   }
-  if (tid < C) s_bias[tid] = (MODE == 0) ? bias[tid] : 0.f;
+  if (tid < C) s_bias[tid] = bias[tid];
   if (tid == 0) {
-    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 32); umma::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 4); }
     umma::fence_mbar_init();
   }
@@ -144,84 +120,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
   umma::tc_fence_after_sync();
   const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
-  if (warp < NPROD) {
-    // =========================== producers =====================================================
-    // Warp w owns slabs g = w (mod NPROD) and loads each of them whole; the slab's full barrier
-    // (count 32) is armed with cp.async.mbarrier.arrive.noinc, so a slab is published by the
-    // hardware when its copies land and the warp never blocks on its own loads: up to RING slabs
-    // are in flight per SM.
-    uint32_t g = 0;                      // global slab counter
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
-      const int ho0 = hs * ROWS;
-      const int rows = min(ROWS, Ho - ho0);
-      const int nslabs = (rows - 1) * STRIDE + 3;
-      const int r0 = ho0 * STRIDE - 1;                 // first input row
-      const int c0 = wt * TILE_M * STRIDE - 1;         // first input column
-      const __nv_bfloat16* img = in + (size_t)b * H * W * C;
-      for (int s = 0; s < nslabs; ++s, ++g) {
-        if ((g % NPROD) != (uint32_t)warp) continue;
-        const uint32_t slot = g % RING;
-        umma::mbar_wait(&bars->empty[slot], ((g / RING) & 1) ^ 1);
-        const int r = r0 + s;
-        const bool row_ok = (r >= 0) && (r < H);
-        if (!(dbg & 4))
-          load_slab<G::NPIX, STRIDE == 2 ? 4 : 0, PS, 32>(umma::smem_u32(s_slab + slot * G::SLAB_BYTES),
-                                                          img + (size_t)(row_ok ? r : 0) * W * C, row_ok, c0, W, lane);
-        umma::cp_async_mbar_arrive_noinc(&bars->full[slot]);
+  if (warp == 0) {
+    // =========================== producer: one thread, TMA =====================================
+    if (lane == 0) {
+      umma::tma_prefetch_desc(&map_in2);
+      umma::tma_prefetch_desc(&map_in1);
+      uint32_t g = 0;                      // global slab counter
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+        const int ho0 = hs * ROWS;
+        const int rows = min(ROWS, Ho - ho0);
+        const int nslabs = (rows - 1) * 2 + 3;
+        const int r0 = ho0 * 2 - 1;                      // first input row
+        const int c0 = wt * TILE_M * 2 - 1;              // first input column
+        for (int s = 0; s < nslabs; ++s, ++g) {
+          const uint32_t slot = g % RING;
+          umma::mbar_wait(&bars->empty[slot], ((g / RING) & 1) ^ 1);
+          umma::mbar_expect_tx(&bars->full[slot], S2_SLAB_TX);
+          const uint32_t dst = umma::smem_u32(s_slab + slot * S2_SLAB);
+          umma::tma_load_4d(dst, &map_in2, 0, c0, r0 + s, b, &bars->full[slot]);                       // c0, c0+2, ... (128)
+          umma::tma_load_4d(dst + TILE_M * 64, &map_in1, 0, c0 + 2 * TILE_M, r0 + s, b, &bars->full[slot]);   // ... and the 129th
+          umma::tma_load_4d(dst + S2_P0, &map_in2, 0, c0 + 1, r0 + s, b, &bars->full[slot]);           // c0+1, c0+3, ... (128)
+        }
       }
     }
   } else if (warp == MMA_WARP) {
-    // =========================== MMA issuer ====================================================
-    // The whole warp runs this (uniform) loop and one elected lane issues: a lone divergent thread
-    // makes ptxas shuttle every descriptor through R2UR (~90 cycles per tcgen05.mma, measured).
-    {
-      constexpr uint32_t idesc = umma::make_idesc_bf16(TILE_M, C, false, false);
-      const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), PS);     // A: LBO = plane stride, SBO = 128
-      const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), 512);       // B: LBO = 512, SBO = 128
-      uint32_t g0 = 0;            // slab counter at the start of the current item
-      uint32_t waited = 0;        // slabs [0, waited) are known to be full
-      uint32_t row_ctr = 0;       // global output-row counter (accumulator ring)
-      for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int hs = (it / wtiles) % hsegs;
-        const int rows = min(ROWS, Ho - hs * ROWS);
-        const int nslabs = (rows - 1) * STRIDE + 3;
-        for (int j = 0; j < rows; ++j, ++row_ctr) {
-          const uint32_t need = g0 + j * STRIDE + 3;
-          for (; waited < need; ++waited) umma::mbar_wait(&bars->full[waited % RING], (waited / RING) & 1);
-          umma::fence_proxy_async_smem();     // cp.async (generic proxy) writes -> UMMA (async proxy) reads
-          const uint32_t buf = row_ctr % NACC;
-          umma::mbar_wait(&bars->acc_empty[buf], ((row_ctr / NACC) & 1) ^ 1);
-          umma::tc_fence_after_sync();
-          const uint32_t d_tmem = tmem + buf * 32;
-          constexpr uint32_t a_hi = umma::desc_hi(128), b_hi = umma::desc_hi(128);
-          if (!(dbg & 1) && umma::elect_one())
+    // =========================== MMA issuer (whole warp loops, elected lane issues) ===============
+    constexpr uint32_t idesc = umma::make_idesc_bf16(TILE_M, C, false, false);
+    constexpr uint32_t a_hi = umma::desc_hi_sw64(512), b_hi = umma::desc_hi(128);
+    const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), 0);        // A: K-major SWIZZLE_64B (one span covers K = 32)
+    const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), 512);         // B: LBO = 512, SBO = 128
+    uint32_t g0 = 0;            // slab counter at the start of the current item
+    uint32_t waited = 0;        // slabs [0, waited) are known to be full
+    uint32_t row_ctr = 0;       // global output-row counter (accumulator ring)
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int hs = (it / wtiles) % hsegs;
+      const int rows = min(ROWS, Ho - hs * ROWS);
+      const int nslabs = (rows - 1) * 2 + 3;
+      for (int j = 0; j < rows; ++j, ++row_ctr) {
+        const uint32_t need = g0 + j * 2 + 3;
+        for (; waited < need; ++waited) umma::mbar_wait(&bars->full[waited % RING], (waited / RING) & 1);
+        const uint32_t buf = row_ctr % NACC;
+        umma::mbar_wait(&bars->acc_empty[buf], ((row_ctr / NACC) & 1) ^ 1);
+        umma::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem + buf * 32;
+        if (umma::elect_one()) {
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t slab_lo = a_lo0 + ((g0 + j * STRIDE + kh) % RING) * (G::SLAB_BYTES >> 4);
+            const uint32_t slab_lo = a_lo0 + ((g0 + j * 2 + kh) % RING) * (S2_SLAB >> 4);
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              // stride 2: kw 0 -> even[i], 1 -> odd[i], 2 -> even[i+1]
-              const int a_off = STRIDE == 1 ? kw * 16 : (kw == 1 ? 4 * PS : 0) + (kw == 2 ? 16 : 0);
+              // kw 0 -> plane 0 [i], 1 -> plane 1 [i], 2 -> plane 0 [i + 1]
+              const int a_off = (kw == 1 ? S2_P0 : 0) + (kw == 2 ? 64 : 0);
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks)
-                umma::mma_bf16_lohi(d_tmem, slab_lo + ((a_off + (2 * ks) * PS) >> 4), a_hi,
-                                    b_lo0 + (((kh * 3 + kw) * 4 + 2 * ks) * 512 >> 4), b_hi, idesc,
-                                    (kh | kw | ks) ? 1u : 0u);
+                umma::mma_bf16_lohi(d_tmem, slab_lo + ((a_off + ks * 32) >> 4), a_hi,
+                                    b_lo0 + (((kh * 3 + kw) * 4 + 2 * ks) * 512 >> 4), b_hi, idesc, (kh | kw | ks) ? 1u : 0u);
             }
           }
-          if (umma::elect_one()) {
-            umma::mma_commit(&bars->acc_full[buf]);
-            // input rows that no later output row of this item reads
-            const int nrel = (j == rows - 1) ? 3 : STRIDE;
-            for (int q = 0; q < nrel; ++q) umma::mma_commit(&bars->empty[(g0 + j * STRIDE + q) % RING]);
-          }
-          __syncwarp();
+          umma::mma_commit(&bars->acc_full[buf]);
+          // input rows that no later output row of this item reads
+          const int nrel = (j == rows - 1) ? 3 : 2;
+          for (int q = 0; q < nrel; ++q) umma::mma_commit(&bars->empty[(g0 + j * 2 + q) % RING]);
         }
-        g0 += nslabs;
+        __syncwarp();
       }
+      g0 += nslabs;
     }
-  } else {
+  } else if (warp > MMA_WARP) {
     // =========================== epilogue (warps 5..8) =========================================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
     uint32_t row_ctr = 0;
@@ -233,11 +199,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
       for (int j = 0; j < rows; ++j, ++row_ctr) {
         const uint32_t buf = row_ctr % NACC;
         const size_t off = (((size_t)b * Ho + ho0 + j) * Wo + (wo < Wo ? wo : 0)) * C;
-        uint4 mk[4];
-        if (MODE == 1 && mask != nullptr) {      // in flight while this warp waits for the MMAs
-#pragma unroll
-          for (int gq = 0; gq < 4; ++gq) mk[gq] = __ldg(reinterpret_cast<const uint4*>(mask + off) + gq);
-        }
         mbar_wait_relaxed(&bars->acc_full[buf], (row_ctr / NACC) & 1);
         umma::tc_fence_after_sync();
         uint32_t r[32];
@@ -245,26 +206,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
         umma::tmem_ld_wait();
         umma::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) umma::mbar_arrive(&bars->acc_empty[buf]);
-        if (wo < Wo && !(dbg & 2)) {
+        if (lane == 0) umma::mbar_arrive_relaxed(&bars->acc_empty[buf]);   // relaxed: a release arrive would first drain this warp's outstanding global stores
+        if (wo < Wo) {
           float v[C];
 #pragma unroll
-          for (int k = 0; k < C; ++k) v[k] = __uint_as_float(r[k]);
-          if (MODE == 0) {
-#pragma unroll
-            for (int k = 0; k < C; ++k) v[k] = fmaxf(v[k] + s_bias[k], 0.f);
-          } else if (mask) {
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&mk[gq]);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 m = __bfloat1622float2(h2[k]);
-                v[gq * 8 + 2 * k] = m.x > 0.f ? v[gq * 8 + 2 * k] : 0.f;
-                v[gq * 8 + 2 * k + 1] = m.y > 0.f ? v[gq * 8 + 2 * k + 1] : 0.f;
-              }
-            }
-          }
+          for (int k = 0; k < C; ++k) v[k] = fmaxf(__uint_as_float(r[k]) + s_bias[k], 0.f);
           store_pixel32(out + off, v);
         }
       }
@@ -276,20 +222,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_c32_tc_kernel(const __nv_
   if (warp == MMA_WARP) umma::tmem_dealloc(tmem, NACC * 32);
 }
 
-template <int STRIDE, int MODE>
-int launch(const void* in, const float* w, const float* bias, const void* mask, void* out, int B, int H, int W,
-           cudaStream_t st) {
-  using G = Geo<STRIDE>;
-  const int Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
+int launch_s2_fwd(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, cudaStream_t st) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int items = B * ((Wo + TILE_M - 1) / TILE_M) * ((Ho + ROWS - 1) / ROWS);
-  auto k = conv3x3_c32_tc_kernel<STRIDE, MODE>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-  if (e != cudaSuccess) return dd::fail((int)e, "conv_tc: cudaFuncSetAttribute(%d): %s", G::SMEM, cudaGetErrorString(e));
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_s2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM);
+  if (e != cudaSuccess) return dd::fail((int)e, "conv_tc s2: cudaFuncSetAttribute(%d): %s", S2_SMEM, cudaGetErrorString(e));
+  CUtensorMap m2, m1;
+  int r = dd::tma_map_nhwc_sw64(&m2, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, 255, 2);      // 255 source pixels -> 128 loaded
+  if (!r) r = dd::tma_map_nhwc_sw64(&m1, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, 1, 1);
+  if (r) return dd::fail(DD_ERR_UNSUPPORTED, "conv_tc s2: cuTensorMapEncodeTiled -> %d (B %d H %d W %d)", r, B, H, W);
   const int grid = items < dd::kSMs ? items : dd::kSMs;
-  static const int dbg = getenv("DD_CONV_DBG") ? atoi(getenv("DD_CONV_DBG")) : 0;   // profiling aid: 1 no MMA, 2 no stores, 4 no loads
-  k<<<grid, NTHREADS, G::SMEM, st>>>((const __nv_bfloat16*)in, w, bias, (const __nv_bfloat16*)mask,
-                                     (__nv_bfloat16*)out, B, H, W, Ho, Wo, dbg);
-  return dd::check_launch("conv3x3_c32_tc");
+  conv3x3_c32_s2_tc_kernel<<<grid, NTHREADS, S2_SMEM, st>>>(m2, m1, w, bias, (__nv_bfloat16*)out, B, H, W, Ho, Wo);
+  return dd::check_launch("conv3x3_c32_s2_tc");
 }
 
 
@@ -330,15 +274,6 @@ constexpr int S1_SMEM = W_BYTES + S1_RING * S1_SLAB + 1024;
 constexpr int S1_THREADS = 32 * (NPROD + 1 + S1_EPI);
 static_assert(NPROD == 4, "one slab of every quad per producer warp");
 
-#ifdef DD_S1_PROF
-__device__ long long g_s1_prof[148 * 16];
-#define S1_T(var) const long long var = clock64()
-#define S1_ACC(i, d) prof[i] += (d)
-#else
-#define S1_T(var)
-#define S1_ACC(i, d)
-#endif
-
 struct S1Bars {
   uint64_t full[S1_NQUAD], empty[S1_NQUAD], acc_full[S1_NGRP], acc_empty[S1_NGRP];
   uint32_t tmem_base;
@@ -350,7 +285,7 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
                                                                            const float* __restrict__ bias,
                                                                            const __nv_bfloat16* __restrict__ mask,
                                                                            __nv_bfloat16* __restrict__ out, int B, int H,
-                                                                           int W, int dbg) {
+                                                                           int W) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_slab = smem + W_BYTES;
@@ -426,40 +361,26 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
     const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), S1_WN);         // B: LBO = channel-group block, SBO = 128
     uint32_t g = 0;             // slab counter
     uint32_t rc0 = 0;           // output-row counter at the start of the item (accumulator ring position)
-#ifdef DD_S1_PROF
-    long long prof[6] = {0, 0, 0, 0, 0, 0};
-    const long long t_begin = clock64();
-#endif
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int hs = (it / wtiles) % hsegs;
       const int rows = min(S1_ROWS, H - hs * S1_ROWS);
       const bool last_item = it + (int)gridDim.x >= items;
       for (int s = 0; s < rows + 2; ++s, ++g) {
         // input row s of the item feeds output rows s-2 (kh = 2), s-1 (kh = 1), s (kh = 0)
-        S1_T(t0);
         const bool is_new = s < rows;                     // output row s receives its first contribution
         if ((g & 3) == 0) {                               // first slab of a quad
           const uint32_t quad = g >> 2;
           umma::mbar_wait(&bars->full[quad % S1_NQUAD], (quad / S1_NQUAD) & 1);   // TMA writes: async proxy, no fence needed
-#ifdef DD_S1_PROF
-          { const long long d = clock64() - t0; prof[2] += d; if (d > 400) prof[3] += 1; }
-#endif
         }
-        S1_T(t0b);
         if (is_new && ((rc0 + s) & 3) == 0) {             // first row of an accumulator group
           const uint32_t grp = (rc0 + s) >> 2;
           umma::mbar_wait(&bars->acc_empty[grp % S1_NGRP], ((grp / S1_NGRP) & 1) ^ 1);
           umma::tc_fence_after_sync();
-#ifdef DD_S1_PROF
-          { const long long d = clock64() - t0b; prof[5] += d; if (d > 400) prof[3] += 1000000; }
-#endif
         }
-        S1_T(t1);
         const uint32_t slab_lo = a_lo0 + (g % S1_RING) * (S1_SLAB >> 4);
         const uint32_t rc_done = rc0 + s - 2;             // output row completed by this batch (s >= 2)
         if (umma::elect_one()) {
-          if (dbg & 1) {
-          } else if (s >= 2 && is_new) {
+          if (s >= 2 && is_new) {
             // ---- interior row (62 of 66): three output rows in ring slots sl, sl+1, sl+2; straight-line issue ----
             const uint32_t sl = rc_done % S1_NACC;
             const uint32_t d0 = tmem + sl * 32;
@@ -520,19 +441,9 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
             umma::mma_commit(&bars->acc_full[(rc_done >> 2) % S1_NGRP]);
         }
         __syncwarp();
-        S1_T(t2);
-        S1_ACC(0, t1 - t0); S1_ACC(1, t2 - t1);
       }
       rc0 += rows;
     }
-#ifdef DD_S1_PROF
-    if (lane == 0) {
-      prof[4] = clock64() - t_begin;
-      for (int i = 0; i < 5; ++i) g_s1_prof[blockIdx.x * 16 + i] = prof[i];
-      g_s1_prof[blockIdx.x * 16 + 5] = g;
-      g_s1_prof[blockIdx.x * 16 + 6] = prof[5];
-    }
-#endif
   } else {
     // =========================== epilogue (warps 5..12) ===========================================
     // TMEM -> registers (thread = pixel) -> bias/ReLU (or ReLU mask) -> bf16 -> two 32-byte stores per thread.
@@ -547,10 +458,6 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
     for (int k = 0; k < C; ++k) bs[k] = s_bias[k];
     uint32_t rc0 = 0;
     uint32_t cur_grp = 0xffffffffu;                        // accumulator group this warp is reading
-#ifdef DD_S1_PROF
-    long long eprof[3] = {0, 0, 0};
-    const long long te_begin = clock64();
-#endif
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
       const int h0 = hs * S1_ROWS;
@@ -567,7 +474,6 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
           umma::ldg256(mask + off, mk);
           umma::ldg256(mask + off + 16, mk + 8);
         }
-        S1_T(e0);
         if (grp != cur_grp) {
           if (cur_grp != 0xffffffffu) {          // both rows of the previous group are in registers
             umma::tc_fence_before_sync();
@@ -578,12 +484,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
           umma::tc_fence_after_sync();
           cur_grp = grp;
         }
-        S1_T(e1);
         uint32_t r[32];
         umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * 32, r);
         umma::tmem_ld_wait();
-        S1_T(e2);
-        if (ok && !(dbg & 2)) {
+        if (ok) {
           uint32_t pk[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -599,21 +503,10 @@ __global__ void __launch_bounds__(S1_THREADS, 1) conv3x3_c32_s1_tc_kernel(const 
           umma::stg256(out + off, pk);
           umma::stg256(out + off + 16, pk + 8);
         }
-#ifdef DD_S1_PROF
-        { S1_T(e3); eprof[0] += e1 - e0; eprof[1] += e2 - e1; eprof[2] += e3 - e2; }
-#endif
       }
       rc0 += rows;
     }
     // (the last group is never waited for by the MMA warp: no arrival owed)
-#ifdef DD_S1_PROF
-    if (lane == 0 && ew == 0) {
-      g_s1_prof[blockIdx.x * 16 + 8] = eprof[0];
-      g_s1_prof[blockIdx.x * 16 + 9] = eprof[1];
-      g_s1_prof[blockIdx.x * 16 + 10] = eprof[2];
-      g_s1_prof[blockIdx.x * 16 + 11] = clock64() - te_begin;
-    }
-#endif
   }
   umma::tc_fence_before_sync();
   __syncthreads();
@@ -628,12 +521,11 @@ int launch_s1(const void* in, const float* w, const float* bias, const void* mas
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_SMEM);
   if (e != cudaSuccess) return dd::fail((int)e, "conv_tc s1: cudaFuncSetAttribute(%d): %s", S1_SMEM, cudaGetErrorString(e));
   const int grid = items < dd::kSMs ? items : dd::kSMs;
-  static const int dbg = getenv("DD_CONV_DBG") ? atoi(getenv("DD_CONV_DBG")) : 0;   // profiling aid: 1 no MMA, 2 no stores
   if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return dd::fail(DD_ERR_ALIGNMENT, "conv_tc s1: input is not 16-byte aligned");
   CUtensorMap map;
   if (int r = dd::tma_map_nhwc_sw64(&map, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, 130))
     return dd::fail(DD_ERR_UNSUPPORTED, "conv_tc s1: cuTensorMapEncodeTiled -> %d (B %d H %d W %d)", r, B, H, W);
-  k<<<grid, S1_THREADS, S1_SMEM, st>>>(map, w, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H, W, dbg);
+  k<<<grid, S1_THREADS, S1_SMEM, st>>>(map, w, bias, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H, W);
   return dd::check_launch("conv3x3_c32_s1_tc");
 }
 
@@ -648,6 +540,7 @@ int launch_s1(const void* in, const float* w, const float* bias, const void* mas
 // ================================================================================================
 constexpr int DG_MROWS = 16;      // dy rows per work item (32 dx rows)
 constexpr int DG_SMEM = W_BYTES + RING * 4 * PS + 1024;
+constexpr int DG_THREADS = 32 * (NPROD + 1 + 8);      // 8 epilogue warps: two per TMEM lane quarter, one per dx row of the pair
 
 struct DgBars {
   uint64_t full[RING], empty[RING], acc_full[2], acc_empty[2];
@@ -672,14 +565,14 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
   const int items = B * wtiles * hsegs;
 
   // B operand of tap t: [n = ci][k = co] = W[co][ci][t]
-  for (int i = tid; i < 9 * C * C; i += NTHREADS) {
+  for (int i = tid; i < 9 * C * C; i += DG_THREADS) {
     const int co = i & 31, ci = (i >> 5) & 31, tap = i >> 10;
     *reinterpret_cast<__nv_bfloat16*>(s_w + (tap * 4 + (co >> 3)) * 512 + ci * 16 + (co & 7) * 2) =
         __float2bfloat16_rn(w_oihw[(co * C + ci) * 9 + tap]);
   }
   if (tid == 0) {
     for (int i = 0; i < RING; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 8); }
     umma::fence_mbar_init();
   }
   if (warp == MMA_WARP) umma::tmem_alloc(&bars->tmem_base, 256);
@@ -691,7 +584,8 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
 
   if (warp < NPROD) {
     // =========================== producer: dy rows m0 .. m0+rows, one thread, TMA ===============
-    // four [129 px][8 ch] boxes per dy row; rows >= Ho and columns >= Wo are zero-filled by the TMA unit
+    // ONE whole-pixel box [129 px][32 ch] per dy row (64-byte swizzle: the K-major SWIZZLE_64B operand; full sectors from L2,
+    // one request per row); rows >= Ho and columns >= Wo are zero-filled by the TMA unit
     if (warp == 0 && lane == 0) {
       umma::tma_prefetch_desc(&map_dy);
       uint32_t g = 0;
@@ -703,10 +597,8 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
         for (int s = 0; s <= rows; ++s, ++g) {
           const uint32_t slot = g % RING;
           umma::mbar_wait(&bars->empty[slot], ((g / RING) & 1) ^ 1);
-          umma::mbar_expect_tx(&bars->full[slot], 4 * 129 * 16);
-          const uint32_t dst = umma::smem_u32(s_slab + slot * SLAB);
-#pragma unroll
-          for (int cg = 0; cg < 4; ++cg) umma::tma_load_4d(dst + cg * PS, &map_dy, cg * 8, i0, m0 + s, b, &bars->full[slot]);
+          umma::mbar_expect_tx(&bars->full[slot], 129 * 64);
+          umma::tma_load_4d(umma::smem_u32(s_slab + slot * SLAB), &map_dy, 0, i0, m0 + s, b, &bars->full[slot]);
         }
       }
     }
@@ -714,9 +606,9 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
     {
       // =========================== MMA issuer (whole warp, elected lane issues) =================
       constexpr uint32_t idesc = umma::make_idesc_bf16(TILE_M, C, false, false);
-      const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), PS);
+      const uint32_t a_lo0 = umma::desc_lo(umma::smem_u32(s_slab), 0);          // A: K-major SWIZZLE_64B
       const uint32_t b_lo0 = umma::desc_lo(umma::smem_u32(s_w), 512);
-      constexpr uint32_t ab_hi = umma::desc_hi(128);
+      constexpr uint32_t a_hi = umma::desc_hi_sw64(512), b_hi = umma::desc_hi(128);
       // {accumulator (0: row 2m even, 1: row 2m odd, 2: row 2m+1 even, 3: row 2m+1 odd), kh, kw, slab (0: m, 1: m+1), shift}
       constexpr int T[9][5] = {{0, 1, 1, 0, 0}, {1, 1, 0, 0, 1}, {1, 1, 2, 0, 0}, {2, 0, 1, 1, 0}, {2, 2, 1, 0, 0},
                                {3, 0, 0, 1, 1}, {3, 0, 2, 1, 0}, {3, 2, 0, 0, 1}, {3, 2, 2, 0, 0}};
@@ -739,8 +631,8 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
             const bool first_of_acc = (t == 0) || (T[t][0] != T[t - (t > 0 ? 1 : 0)][0]);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
-              umma::mma_bf16_lohi(d0 + a * 32, slab_lo[T[t][3]] + T[t][4] + ((2 * ks) * PS >> 4), ab_hi,
-                                  b_lo0 + ((tap * 4 + 2 * ks) * 512 >> 4), ab_hi, idesc,
+              umma::mma_bf16_lohi(d0 + a * 32, slab_lo[T[t][3]] + ((T[t][4] * 64 + ks * 32) >> 4), a_hi,
+                                  b_lo0 + ((tap * 4 + 2 * ks) * 512 >> 4), b_hi, idesc,
                                   (first_of_acc && ks == 0) ? 0u : 1u);
           }
           if (umma::elect_one()) {
@@ -754,8 +646,11 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) =========================================
+    // =========================== epilogue (warps 5..12) ========================================
+    // two warps per TMEM lane quarter: warp `half` takes dx row 2m + half (accumulators 2*half: even columns, 2*half + 1: odd),
+    // so that each thread stores two adjacent pixels (128 contiguous bytes) after the ReLU mask of the layer input
     const int quarter = warp & 3;
+    const int half = (warp - (NPROD + 1)) >> 2;
     uint32_t mctr = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
@@ -764,27 +659,29 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
       const int i = wt * TILE_M + quarter * 32 + lane;
       for (int j = 0; j < rows; ++j, ++mctr) {
         const uint32_t set = mctr & 1;
-        uint4 mk[4][4];
+        uint4 mk[2][4];
         if (mask != nullptr) {
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
+          for (int aa = 0; aa < 2; ++aa) {
+            const int a = 2 * half + aa;
             const int h = 2 * (m0 + j) + (a >> 1), w = 2 * i + (a & 1);
             const size_t moff = (((size_t)b * H + (h < H ? h : 0)) * W + (w < W ? w : 0)) * C;
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) mk[a][gq] = __ldg(reinterpret_cast<const uint4*>(mask + moff) + gq);
+            for (int gq = 0; gq < 4; ++gq) mk[aa][gq] = __ldg(reinterpret_cast<const uint4*>(mask + moff) + gq);
           }
         }
         mbar_wait_relaxed(&bars->acc_full[set], (mctr >> 1) & 1);
         umma::tc_fence_after_sync();
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int aa = 0; aa < 2; ++aa) {
+          const int a = 2 * half + aa;
           uint32_t r[32];
           umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + set * 128 + a * 32, r);
           umma::tmem_ld_wait();
-          if (a == 3) {            // all four accumulators of this set are in registers / stored
+          if (aa == 1) {           // both accumulators of this warp's dx row are in registers / stored
             umma::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&bars->acc_empty[set]);
+            if (lane == 0) umma::mbar_arrive_relaxed(&bars->acc_empty[set]);
           }
           const int h = 2 * (m0 + j) + (a >> 1), w = 2 * i + (a & 1);
           if (h < H && w < W) {
@@ -795,7 +692,7 @@ __global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_con
             if (mask) {
 #pragma unroll
               for (int gq = 0; gq < 4; ++gq) {
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&mk[a][gq]);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&mk[aa][gq]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const float2 m = __bfloat1622float2(h2[k]);
@@ -999,7 +896,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __
         umma::tmem_ld_wait();
         umma::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) umma::mbar_arrive(&bars->acc_empty[buf]);
+        if (lane == 0) umma::mbar_arrive_relaxed(&bars->acc_empty[buf]);   // relaxed: a release arrive would first drain this warp's outstanding global stores
         if (wo < Wm) {
           __nv_bfloat16* dst = out + (((size_t)b * H + h0 + j) * Wm + wo) * C;
           float v[C];
@@ -1018,11 +915,6 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __
 
 }  // namespace
 
-#ifdef DD_S1_PROF
-extern "C" int dd_debug_s1_prof(long long* host) {
-  return (int)cudaMemcpyFromSymbol(host, g_s1_prof, sizeof(long long) * 148 * 16);
-}
-#endif
 
 namespace dd {
 
@@ -1038,10 +930,9 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
   // the epilogues store (and read the ReLU mask) in 32-byte pieces; the producers read 16-byte pieces
   if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask)) & 31) != 0 || (reinterpret_cast<uintptr_t>(in) & 15) != 0)
     return fail(DD_ERR_ALIGNMENT, "conv_tc: activations must be 32-byte aligned (in %p, out %p, mask %p)", in, out, mask);
-  static const bool old_s1 = getenv("DD_CONV_OLD_S1") != nullptr;   // A/B timing aid: the 18 x N=32 gather kernel
-  if (mode == 0 && stride == 1) return old_s1 ? launch<1, 0>(in, w, bias, nullptr, out, B, H, W, st) : launch_s1<0>(in, w, bias, nullptr, out, B, H, W, st);
-  if (mode == 0 && stride == 2) return launch<2, 0>(in, w, bias, nullptr, out, B, H, W, st);
-  if (mode == 1 && stride == 1) return old_s1 ? launch<1, 1>(in, w, nullptr, mask, out, B, H, W, st) : launch_s1<1>(in, w, nullptr, mask, out, B, H, W, st);
+  if (mode == 0 && stride == 1) return launch_s1<0>(in, w, bias, nullptr, out, B, H, W, st);
+  if (mode == 0 && stride == 2) return launch_s2_fwd(in, w, bias, out, B, H, W, st);
+  if (mode == 1 && stride == 1) return launch_s1<1>(in, w, nullptr, mask, out, B, H, W, st);
   if (mode == 1 && stride == 2) {
     // here `in` = dy [B,Ho,Wo,32], `out` = dx [B,H,W,32]
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
@@ -1050,9 +941,9 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
     if (e != cudaSuccess) return fail((int)e, "dgrad_s2_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return fail(DD_ERR_ALIGNMENT, "dgrad_s2_tc: dy is not 16-byte aligned");
     CUtensorMap mdy;
-    if (int r = tma_map_nhwc_c8(&mdy, in, (uint64_t)B, (uint64_t)Ho, (uint64_t)Wo, 129))
+    if (int r = tma_map_nhwc_sw64(&mdy, in, (uint64_t)B, (uint64_t)Ho, (uint64_t)Wo, 129))
       return fail(DD_ERR_UNSUPPORTED, "dgrad_s2_tc: cuTensorMapEncodeTiled -> %d", r);
-    conv3x3_c32_dgrad_s2_tc_kernel<<<items < kSMs ? items : kSMs, NTHREADS, DG_SMEM, st>>>(
+    conv3x3_c32_dgrad_s2_tc_kernel<<<items < kSMs ? items : kSMs, DG_THREADS, DG_SMEM, st>>>(
         mdy, w, (const __nv_bfloat16*)mask, (__nv_bfloat16*)out, B, H, W, Ho, Wo);
     return check_launch("conv3x3_c32_dgrad_s2_tc");
   }
