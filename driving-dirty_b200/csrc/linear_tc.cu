@@ -196,10 +196,27 @@ __global__ void split_fold_kernel(const float* __restrict__ partial, const float
 // wgrad: dW[n][k] (+)= sum_b dy[b][n] x[b][k]; one 128 x KT output tile per stage (no accumulation across
 // stages), written straight from TMEM to HBM.
 // ------------------------------------------------------------------------------------------------
-constexpr int W_STAGES = 4;
+constexpr int W_STAGES = 3;
 constexpr int W_STAGE_BYTES = 4 * BOX + 8 * BOX;     // dy^T: 4 boxes of 32 n; x: up to 8 boxes of 32 k
 constexpr int W_TPAD = 36;                           // floats per row of a warp's 32 x 32 transpose block
-constexpr int W_SMEM = W_STAGES * W_STAGE_BYTES + 4 * 32 * W_TPAD * 4 + 2048;
+constexpr int W_EPI = 8;                             // epilogue warps: two per TMEM lane quarter, alternate 32-column chunks
+constexpr int W_THREADS = 32 * (2 + W_EPI);
+constexpr int W_SMEM = W_STAGES * W_STAGE_BYTES + W_EPI * 32 * W_TPAD * 4 + 2048;
+
+// Adam folded into the weight-gradient epilogue (world size 1): the gradient tile never goes to HBM -- the epilogue reads
+// the weight and its two moments where it would have written dW, and writes them back updated: 24 bytes per parameter
+// instead of 4 (dW write) + 28 (a separate Adam pass).  Same arithmetic as csrc/adam.cu (torch.optim.Adam, amsgrad off).
+struct AdamFuse {
+  float* p; float* m; float* v;          // weight [N][K], exp_avg, exp_avg_sq (same layout); p == nullptr: plain weight gradient
+  float beta1, beta2, eps, step_size, inv_sqrt_bc2, weight_decay;
+};
+__device__ __forceinline__ float adam_fused_one(float p, float g, float& m, float& v, const AdamFuse& h) {
+  if (h.weight_decay != 0.f) g = fmaf(h.weight_decay, p, g);
+  m = m + (1.f - h.beta1) * (g - m);
+  v = h.beta2 * v + (1.f - h.beta2) * g * g;
+  const float denom = sqrtf(v) * h.inv_sqrt_bc2 + h.eps;
+  return p - h.step_size * (m / denom);
+}
 
 struct WgradBars {
   uint64_t full[W_STAGES], empty[W_STAGES], acc_full[2], acc_empty[2];
@@ -211,15 +228,16 @@ struct WgradGeo {
   long long K;
   int n_tiles, k_tiles, KT;      // KT = 128 or 256 columns per tile
   int accumulate;
+  AdamFuse adam;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy,
-                                                                     const __grid_constant__ CUtensorMap map_x,
-                                                                     float* __restrict__ dw, WgradGeo g) {
+__global__ void __launch_bounds__(W_THREADS, 1) linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy,
+                                                                       const __grid_constant__ CUtensorMap map_x,
+                                                                       float* __restrict__ dw, const WgradGeo g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   float* stage_out = reinterpret_cast<float*>(smem + W_STAGES * W_STAGE_BYTES);
-  WgradBars* bars = reinterpret_cast<WgradBars*>(smem + W_STAGES * W_STAGE_BYTES + 4 * 32 * W_TPAD * 4);
+  WgradBars* bars = reinterpret_cast<WgradBars*>(smem + W_STAGES * W_STAGE_BYTES + W_EPI * 32 * W_TPAD * 4);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const long long items = (long long)g.n_tiles * g.k_tiles;
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_wgrad_tc_kernel(const __gri
 
   if (tid == 0) {
     for (int i = 0; i < W_STAGES; ++i) { umma::mbar_init(&bars->full[i], 1); umma::mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->acc_full[i], 1); umma::mbar_init(&bars->acc_empty[i], W_EPI); }
     umma::fence_mbar_init();
     umma::tma_prefetch_desc(&map_dy);
     umma::tma_prefetch_desc(&map_x);
@@ -275,6 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_wgrad_tc_kernel(const __gri
     }
   } else {
     const int quarter = warp & 3;
+    const int sub = (warp - 2) >> 2;               // which of the quarter's two warps: takes the 32-column chunks of its parity
     uint32_t c = 0;
     for (long long it = blockIdx.x; it < items; it += gridDim.x, ++c) {
       const int ni = (int)(it / g.k_tiles), ki = (int)(it % g.k_tiles);
@@ -283,8 +302,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_wgrad_tc_kernel(const __gri
       umma::tc_fence_after_sync();
       const int n0 = ni * 128 + quarter * 32;
       const long long k0 = (long long)ki * g.KT;
-      float* blk = stage_out + quarter * (32 * W_TPAD);
-      for (int cb = 0; cb < g.KT; cb += 32) {
+      float* blk = stage_out + (warp - 2) * (32 * W_TPAD);
+      for (int cb = 32 * sub; cb < g.KT; cb += 64) {
         uint32_t v[32];
         umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + a * 256 + cb, v);
         umma::tmem_ld_wait();
@@ -298,6 +317,42 @@ __global__ void __launch_bounds__(THREADS, 1) linear_wgrad_tc_kernel(const __gri
                           __uint_as_float(v[4 * q + 3]));
         __syncwarp();
         const int cq = lane & 7;
+        if (g.adam.p != nullptr) {
+          // fused Adam: all eight rows of the chunk at once -> 24 independent 16-byte loads per thread in flight (with
+          // four rows per batch the kernel sat at 4.1 TB/s: ~49 KB in flight per SM do not cover the loaded-DRAM latency)
+          {
+            float4 pp[8], mm[8], vv[8];
+            bool ok[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int r = (lane >> 3) + 4 * q;
+              const int n = n0 + r;
+              const long long k = k0 + cb + 4 * cq;
+              ok[q] = n < g.N && k < g.K;
+              if (ok[q]) {
+                const size_t e = (size_t)n * g.K + k;
+                pp[q] = *reinterpret_cast<const float4*>(g.adam.p + e);
+                mm[q] = __ldcs(reinterpret_cast<const float4*>(g.adam.m + e));
+                vv[q] = __ldcs(reinterpret_cast<const float4*>(g.adam.v + e));
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (!ok[q]) continue;
+              const int r = (lane >> 3) + 4 * q;
+              const size_t e = (size_t)(n0 + r) * g.K + (k0 + cb + 4 * cq);
+              const float4 gr = *reinterpret_cast<const float4*>(blk + r * W_TPAD + 4 * cq);
+              pp[q].x = adam_fused_one(pp[q].x, gr.x, mm[q].x, vv[q].x, g.adam);
+              pp[q].y = adam_fused_one(pp[q].y, gr.y, mm[q].y, vv[q].y, g.adam);
+              pp[q].z = adam_fused_one(pp[q].z, gr.z, mm[q].z, vv[q].z, g.adam);
+              pp[q].w = adam_fused_one(pp[q].w, gr.w, mm[q].w, vv[q].w, g.adam);
+              *reinterpret_cast<float4*>(g.adam.p + e) = pp[q];
+              __stcs(reinterpret_cast<float4*>(g.adam.m + e), mm[q]);
+              __stcs(reinterpret_cast<float4*>(g.adam.v + e), vv[q]);
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
           const int r = (lane >> 3) + 4 * itr;
@@ -425,10 +480,18 @@ int linear_dgrad_tc(const float* dy, const float* w, void* dx, int dx_dtype, voi
   return g.splits > 1 ? check_launch("linear_dgrad_fold") : 0;
 }
 
-// dy fp32 [B][N], x fp32 [B][K] -> dW fp32 [N][K] (overwritten, or accumulated into)
-int linear_wgrad_tc(const float* dy, const float* x, float* dw, int B, int N, long long K, int accumulate, cudaStream_t st) {
-  WgradGeo g;
+// dy fp32 [B][N], x fp32 [B][K] -> dW fp32 [N][K] (overwritten, or accumulated into); with adam_pmv != nullptr the epilogue
+// applies the Adam update to {weight, exp_avg, exp_avg_sq} = adam_pmv[0..2] instead of writing dW (hyper: beta1, beta2,
+// eps, step_size = lr / (1 - beta1^t), inv_sqrt_bc2 = 1 / sqrt(1 - beta2^t), weight_decay)
+int linear_wgrad_tc(const float* dy, const float* x, float* dw, int B, int N, long long K, int accumulate, cudaStream_t st,
+                    float* const* adam_pmv = nullptr, const float* hyper = nullptr) {
+  WgradGeo g = {};
   g.B = B; g.N = N; g.K = K;
+  if (adam_pmv) {
+    g.adam.p = adam_pmv[0]; g.adam.m = adam_pmv[1]; g.adam.v = adam_pmv[2];
+    g.adam.beta1 = hyper[0]; g.adam.beta2 = hyper[1]; g.adam.eps = hyper[2]; g.adam.step_size = hyper[3];
+    g.adam.inv_sqrt_bc2 = hyper[4]; g.adam.weight_decay = hyper[5];
+  }
   g.KT = K >= 256 ? 256 : 128;
   g.n_tiles = ceil_div_ll(N, 128);
   g.k_tiles = ceil_div_ll(K, g.KT);
@@ -440,7 +503,7 @@ int linear_wgrad_tc(const float* dy, const float* x, float* dw, int B, int N, lo
     return fail(DD_ERR_UNSUPPORTED, "linear_wgrad_tc: %s", msg);
   if (int e = set_smem(linear_wgrad_tc_kernel, W_SMEM)) return e;
   const long long items = (long long)g.n_tiles * g.k_tiles;
-  linear_wgrad_tc_kernel<<<(int)(items < kSMs ? items : kSMs), THREADS, W_SMEM, st>>>(mdy, mx, dw, g);
+  linear_wgrad_tc_kernel<<<(int)(items < kSMs ? items : kSMs), W_THREADS, W_SMEM, st>>>(mdy, mx, dw, g);
   return check_launch("linear_wgrad_tc");
 }
 

@@ -232,9 +232,9 @@ class SkinnyLinear(torch.autograd.Function):
     weight-streaming kernels (x is read as fp32)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, impl, grad_buffer=None, grad_ready=None):
+    def forward(ctx, x, w, b, impl, grad_buffer=None, grad_ready=None, fused_update=None):
         _require_cuda(x, w)
-        ctx.grad_buffer, ctx.grad_ready = grad_buffer, grad_ready
+        ctx.grad_buffer, ctx.grad_ready, ctx.fused_update = grad_buffer, grad_ready, fused_update
         x, wd = _c(x), _c(w.detach())
         if wd.dtype != torch.float32:
             wd = wd.float()
@@ -266,6 +266,13 @@ class SkinnyLinear(torch.autograd.Function):
             ws, n = _linear_ws(B, N, K, x.device)
             call("dd_linear_dgrad", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), dtype_code(ctx.x_dtype), ws.data_ptr(), n,
                  B, N, K, ctx.impl, st)
+        if ctx.needs_input_grad[1] and ctx.fused_update is not None and ctx.impl == _lib.IMPL_TCGEN05 and B <= 32 \
+                and x.dtype == torch.float32:
+            # optim.FusedAdam (world size 1) folds this weight's Adam step into the weight-gradient kernel's epilogue: the
+            # gradient never exists in HBM (dd_linear_wgrad_adam); the input gradient above was computed from the old weight
+            db = torch.empty(N, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            ctx.fused_update(dy, x, db)
+            return dx, None, db, None, None, None, None
         if ctx.needs_input_grad[1]:
             # a parameter claimed by optim.FusedAdam's sharded update owns a persistent (peer-mapped) gradient
             # buffer: the kernel writes there and autograd gets no tensor to clone or accumulate
@@ -280,7 +287,7 @@ class SkinnyLinear(torch.autograd.Function):
                     ctx.grad_ready()
         elif ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 def linear(x, weight, bias=None, impl=IMPL_AUTO, allow_tf32=False):
@@ -295,7 +302,8 @@ def linear(x, weight, bias=None, impl=IMPL_AUTO, allow_tf32=False):
     buf = getattr(weight, "_dd_grad_buffer", None)
     if buf is not None and not (buf.shape == weight.shape and buf.dtype == torch.float32 and buf.is_contiguous()):
         raise RuntimeError("linear: weight._dd_grad_buffer does not match the weight")
-    return SkinnyLinear.apply(x, weight, bias, impl, buf, getattr(weight, "_dd_grad_ready", None) if buf is not None else None)
+    return SkinnyLinear.apply(x, weight, bias, impl, buf, getattr(weight, "_dd_grad_ready", None) if buf is not None else None,
+                              getattr(weight, "_dd_fused_update", None) if torch.is_grad_enabled() else None)
 
 
 # --------------------------------------------------------------------------------------------

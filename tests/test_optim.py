@@ -126,3 +126,38 @@ def test_flat_layout_is_aligned_and_disjoint():
     for (o, n), o_next in zip(zip(offs, numels), offs[1:] + [total]):
         assert o + n <= o_next
     assert total % 4 == 0          # shard_bounds works on 16-byte granules
+
+
+@pytest.mark.gpu
+def test_fused_adam_step_inside_the_weight_gradient_kernel():
+    """World size 1: the wide FC weights take their Adam step in the epilogue of ops.linear's tcgen05 weight-gradient kernel
+    (dd_linear_wgrad_adam; the gradient never reaches HBM).  Same weights, moments and bias as the unfused form
+    (weight gradient written, then dd_adam_step) over several steps, with weight decay; p.grad stays None for them."""
+    from driving_dirty_b200 import _lib, ops
+    from driving_dirty_b200.optim import FusedAdam
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(21)
+    N, K, B = 4096, 1028, 32                       # N*K >= 2^22: the tensor-core linear kernels apply
+    w0, b0 = (torch.randn(N, K, generator=g) * 0.05).to(dev), (torch.randn(N, generator=g) * 0.05).to(dev)
+    xs = [torch.randn(B, K, generator=g).to(dev) for _ in range(4)]
+    gys = [torch.randn(B, N, generator=g).to(dev) for _ in range(4)]
+    res = []
+    for fuse in (False, True):
+        w, b = torch.nn.Parameter(w0.clone()), torch.nn.Parameter(b0.clone())
+        opt = FusedAdam([w, b], lr=1e-2, weight_decay=0.01, fuse_into_backward=fuse)
+        for x, gy in zip(xs, gys):
+            opt.zero_grad()
+            xin = x.clone().requires_grad_(True)
+            y = ops.linear(xin, w, b, impl=_lib.IMPL_TCGEN05)
+            y.backward(gy)
+            assert (w.grad is None) == fuse and b.grad is not None and xin.grad is not None
+            opt.step()
+        st = opt.state[w]
+        res.append((w.detach().clone(), b.detach().clone(), st["exp_avg"].clone(), st["exp_avg_sq"].clone(), st["step"], xin.grad.clone()))
+    for a, c in zip(res[0][:4], res[1][:4]):
+        assert float((a.reshape(-1) - c.reshape(-1)).abs().max() / a.abs().max()) < 1e-6
+    assert res[0][4] == res[1][4] == 4
+    assert torch.equal(res[0][5], res[1][5])      # the input gradient used the weight BEFORE its update in both forms
+    # checkpoint layout is unchanged
+    sd = opt.state_dict()
+    assert tuple(sd["state"][0]["exp_avg"].shape) == (N, K) and int(sd["state"][0]["step"]) == 4
