@@ -614,3 +614,70 @@ def test_ats_bounding_boxes_matches_the_reference_loop(dd, n1, n2, seed):
     assert float(got) == float(ref)
     # identical sets: every threshold counts every box (the reference's float32 weighted mean lands an ulp under 1)
     assert float(compute_ats_bounding_boxes(b2.cuda(), b2.cuda())) == float(so.compute_ats_bounding_boxes(b2, b2)[0])
+
+
+# ------------------------------------------------------------------------------- guard bands -
+def test_kernels_stay_inside_their_output_buffers(dd):
+    """compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer_closed.txt), so the out-of-bounds check is our own:
+    every output of the tensor-core kernels sits between two guard bands of a sentinel pattern (ragged shapes: partial
+    column strips, odd row counts, residue classes of different length) and the bands must come back untouched."""
+    import ctypes
+    from driving_dirty_b200 import _lib
+    from driving_dirty_b200._lib import call, stream_ptr
+    st = stream_ptr()
+    GUARD = 4096
+    bands = []
+
+    def guarded(shape, dtype):
+        n = int(np.prod(shape))
+        raw = torch.full((n + 2 * GUARD,), 7.0, device="cuda").to(dtype) if dtype != torch.uint8 else \
+            torch.full((n + 2 * GUARD,), 7, dtype=torch.uint8, device="cuda")
+        bands.append((raw, n))
+        return raw[GUARD: GUARD + n].view(shape)
+
+    B, H, W = 2, 37, 205
+    H3, W3 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    x = torch.rand(B, H, W, 32, device="cuda").bfloat16()
+    dy = (torch.rand(B, H, W, 32, device="cuda") - 0.5).bfloat16()
+    dy3 = (torch.rand(B, H3, W3, 32, device="cuda") - 0.5).bfloat16()
+    w, b = torch.rand(32, 32, 3, 3, device="cuda") * 0.1, torch.zeros(32, device="cuda")
+    n = int(_lib.load().dd_conv_wgrad_workspace_bytes())
+    ws = guarded((n,), torch.uint8)
+    o1, o2 = guarded((B, H, W, 32), torch.bfloat16), guarded((B, H3, W3, 32), torch.bfloat16)
+    call("dd_conv3x3_c32_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), o1.data_ptr(), 1, B, H, W, 1, 2, st)
+    call("dd_conv3x3_c32_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), o2.data_ptr(), 1, B, H, W, 2, 2, st)
+    o3, o4 = guarded((B, H, W, 32), torch.bfloat16), guarded((B, H, W, 32), torch.bfloat16)
+    call("dd_conv3x3_c32_dgrad", dy.data_ptr(), w.data_ptr(), x.data_ptr(), o3.data_ptr(), 1, B, H, W, 1, 2, st)
+    call("dd_conv3x3_c32_dgrad", dy3.data_ptr(), w.data_ptr(), x.data_ptr(), o4.data_ptr(), 1, B, H, W, 2, 2, st)
+    for stride, g in ((1, dy), (2, dy3)):
+        dw, db = guarded((32, 32, 3, 3), torch.float32), guarded((32,), torch.float32)
+        call("dd_conv3x3_c32_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n, 1, B, H, W, stride, 2, st)
+    views = torch.rand(B, 6, 3, 37, 35, device="cuda")          # mosaic 37 x 210
+    a1 = guarded((B, 37, 210, 32), torch.bfloat16)
+    w1 = torch.rand(32, 3, 3, 3, device="cuda")
+    call("dd_conv_c1_fwd", views.data_ptr(), 1, w1.data_ptr(), b.data_ptr(), a1.data_ptr(), 1, B, 37, 210, 2, st)
+    dw1, db1 = guarded((32, 3, 3, 3), torch.float32), guarded((32,), torch.float32)
+    dya = (torch.rand(B, 37, 210, 32, device="cuda") - 0.5).bfloat16()
+    call("dd_conv_c1_wgrad", views.data_ptr(), 1, dya.data_ptr(), 1, dw1.data_ptr(), db1.data_ptr(), ws.data_ptr(), n, B, 37, 210, 2, st)
+    # wide dilated layers: forward, input gradient, weight gradient
+    for (t, cin, cout, k, p, d, hw) in ((1, 96, 64, 7, 0, 7, (9, 23)), (1, 64, 32, 7, 0, 7, (11, 150)), (0, 32, 32, 3, 0, 3, (19, 140))):
+        Hi, Wi = hw
+        Ho = Hi + d * (k - 1) if t else Hi - d * (k - 1)
+        Wo = Wi + d * (k - 1) if t else Wi - d * (k - 1)
+        desc = _lib.ConvDesc(B, cin, cout, Hi, Wi, Ho, Wo, k, k, 1, 1, p, p, d, d, t)
+        xin = torch.rand(B, Hi, Wi, cin, device="cuda").bfloat16()
+        g = (torch.rand(B, Ho, Wo, cout, device="cuda") - 0.5).bfloat16()
+        wt = torch.rand((cin, cout, k, k) if t else (cout, cin, k, k), device="cuda") * 0.05
+        bb = torch.zeros(cout, device="cuda")
+        nn_ = int(_lib.load().dd_conv2d_workspace_bytes(ctypes.byref(desc)))
+        ws2 = guarded((nn_,), torch.uint8)
+        y = guarded((B, Ho, Wo, cout), torch.bfloat16)
+        call("dd_conv2d_fwd", xin.data_ptr(), wt.data_ptr(), bb.data_ptr(), y.data_ptr(), ctypes.byref(desc), 1, 1, ws2.data_ptr(), nn_, st)
+        dxo = guarded((B, Hi, Wi, cin), torch.bfloat16)
+        call("dd_conv2d_dgrad", g.data_ptr(), wt.data_ptr(), xin.data_ptr(), dxo.data_ptr(), ctypes.byref(desc), 1, ws2.data_ptr(), nn_, st)
+        dwo, dbo = guarded(tuple(wt.shape), torch.float32), guarded((cout,), torch.float32)
+        call("dd_conv2d_wgrad", xin.data_ptr(), g.data_ptr(), dwo.data_ptr(), dbo.data_ptr(), ctypes.byref(desc), 1, ws2.data_ptr(), nn_, st)
+    torch.cuda.synchronize()
+    for raw, nel in bands:
+        lo, hi = raw[:GUARD].float(), raw[GUARD + nel:].float()
+        assert bool((lo == 7).all()) and bool((hi == 7).all()), "a kernel wrote outside its output buffer"
