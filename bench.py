@@ -587,6 +587,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         loss = step(resident)
+    opt.synchronize()        # the last step's weight exchange may still be running on the optimizer's side stream: time it too
     e1.record()
     barrier()
     launches = _lib.launch_count() - l0
@@ -623,6 +624,7 @@ def run_ours(args):
         barrier()
         e0.record()
         e2e_loop(args.steps)
+        opt.synchronize()
         e1.record()
         barrier()
         return e0.elapsed_time(e1) * 1e-3

@@ -299,6 +299,10 @@ def linear(x, weight, bias=None, impl=IMPL_AUTO, allow_tf32=False):
         fast = (x.dtype == torch.bfloat16 or allow_tf32) and x.is_cuda and \
             bool(_lib.load().dd_linear_tc_supported(B, weight.shape[0], K))
         impl = _lib.IMPL_TCGEN05 if fast else _lib.IMPL_SIMT
+    ev = getattr(weight, "_dd_ready_event", None)
+    if ev is not None:                 # optim.FusedAdam: this weight's last update may still be landing (side stream)
+        torch.cuda.current_stream().wait_event(ev)
+        weight._dd_ready_event = None
     buf = getattr(weight, "_dd_grad_buffer", None)
     if buf is not None and not (buf.shape == weight.shape and buf.dtype == torch.float32 and buf.is_contiguous()):
         raise RuntimeError("linear: weight._dd_grad_buffer does not match the weight")
