@@ -547,7 +547,9 @@ struct DgBars {
   uint32_t tmem_base;
 };
 
-__global__ void __maxnreg__(104) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_constant__ CUtensorMap map_dy,
+// (96 registers x 416 threads + the optimizer's 96 x 256 update CTA = 64.5 K: both fit one SM's register file, which the
+// overlapped data-parallel update needs -- see csrc/adam.cu)
+__global__ void __maxnreg__(96) conv3x3_c32_dgrad_s2_tc_kernel(const __grid_constant__ CUtensorMap map_dy,
                                                                                const float* __restrict__ w_oihw,
                                                                                const __nv_bfloat16* __restrict__ mask,
                                                                                __nv_bfloat16* __restrict__ dx, int B,

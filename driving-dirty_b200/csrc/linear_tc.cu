@@ -199,9 +199,11 @@ __global__ void split_fold_kernel(const float* __restrict__ partial, const float
 constexpr int W_STAGES = 3;
 constexpr int W_STAGE_BYTES = 4 * BOX + 8 * BOX;     // dy^T: 4 boxes of 32 n; x: up to 8 boxes of 32 k
 constexpr int W_TPAD = 36;                           // floats per row of a warp's 32 x 32 transpose block
-constexpr int W_EPI = 8;                             // epilogue warps: two per TMEM lane quarter, alternate 32-column chunks
-constexpr int W_THREADS = 32 * (2 + W_EPI);
-constexpr int W_SMEM = W_STAGES * W_STAGE_BYTES + W_EPI * 32 * W_TPAD * 4 + 2048;
+// epilogue warps: 4 for the plain weight gradient (192 threads x ~118 registers: co-resides with the data-parallel update CTA
+// of csrc/adam.cu), 8 for the form with Adam folded in (two per TMEM lane quarter, alternate 32-column chunks: it needs
+// the bytes in flight)
+template <bool ADAM> struct WCfg { static constexpr int EPI = ADAM ? 8 : 4; static constexpr int THREADS = 32 * (2 + EPI); };
+constexpr int W_SMEM = W_STAGES * W_STAGE_BYTES + 8 * 32 * W_TPAD * 4 + 2048;
 
 // Adam folded into the weight-gradient epilogue (world size 1): the gradient tile never goes to HBM -- the epilogue reads
 // the weight and its two moments where it would have written dW, and writes them back updated: 24 bytes per parameter
@@ -231,13 +233,15 @@ struct WgradGeo {
   AdamFuse adam;
 };
 
-__global__ void __launch_bounds__(W_THREADS, 1) linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy,
-                                                                       const __grid_constant__ CUtensorMap map_x,
-                                                                       float* __restrict__ dw, const WgradGeo g) {
+template <bool ADAM>
+__global__ void __launch_bounds__(WCfg<ADAM>::THREADS, 1) linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy,
+                                                                                 const __grid_constant__ CUtensorMap map_x,
+                                                                                 float* __restrict__ dw, const WgradGeo g) {
+  constexpr int W_EPI = WCfg<ADAM>::EPI;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   float* stage_out = reinterpret_cast<float*>(smem + W_STAGES * W_STAGE_BYTES);
-  WgradBars* bars = reinterpret_cast<WgradBars*>(smem + W_STAGES * W_STAGE_BYTES + W_EPI * 32 * W_TPAD * 4);
+  WgradBars* bars = reinterpret_cast<WgradBars*>(smem + W_STAGES * W_STAGE_BYTES + 8 * 32 * W_TPAD * 4);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const long long items = (long long)g.n_tiles * g.k_tiles;
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) linear_wgrad_tc_kernel(const __g
     }
   } else {
     const int quarter = warp & 3;
-    const int sub = (warp - 2) >> 2;               // which of the quarter's two warps: takes the 32-column chunks of its parity
+    const int sub = (warp - 2) >> 2;               // ADAM: which of the quarter's two warps (takes the 32-column chunks of its parity)
     uint32_t c = 0;
     for (long long it = blockIdx.x; it < items; it += gridDim.x, ++c) {
       const int ni = (int)(it / g.k_tiles), ki = (int)(it % g.k_tiles);
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) linear_wgrad_tc_kernel(const __g
       const int n0 = ni * 128 + quarter * 32;
       const long long k0 = (long long)ki * g.KT;
       float* blk = stage_out + (warp - 2) * (32 * W_TPAD);
-      for (int cb = 32 * sub; cb < g.KT; cb += 64) {
+      for (int cb = 32 * sub; cb < g.KT; cb += 32 * (W_EPI / 4)) {
         uint32_t v[32];
         umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + a * 256 + cb, v);
         umma::tmem_ld_wait();
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) linear_wgrad_tc_kernel(const __g
                           __uint_as_float(v[4 * q + 3]));
         __syncwarp();
         const int cq = lane & 7;
-        if (g.adam.p != nullptr) {
+        if (ADAM) {
           // fused Adam: all eight rows of the chunk at once -> 24 independent 16-byte loads per thread in flight (with
           // four rows per batch the kernel sat at 4.1 TB/s: ~49 KB in flight per SM do not cover the loaded-DRAM latency)
           {
@@ -351,10 +355,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) linear_wgrad_tc_kernel(const __g
               __stcs(reinterpret_cast<float4*>(g.adam.v + e), vv[q]);
             }
           }
-          continue;
         }
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
+        for (int itr = 0; itr < (ADAM ? 0 : 8); ++itr) {
           const int r = (lane >> 3) + 4 * itr;
           const int n = n0 + r;
           const long long k = k0 + cb + 4 * cq;
@@ -501,9 +504,15 @@ int linear_wgrad_tc(const float* dy, const float* x, float* dw, int B, int N, lo
   if (tma_map_2d_checked(&mdy, dy, 4, B, N, N, 32, 32, true, msg, sizeof msg) ||
       tma_map_2d_checked(&mx, x, 4, B, K, K, 32, 32, true, msg, sizeof msg))
     return fail(DD_ERR_UNSUPPORTED, "linear_wgrad_tc: %s", msg);
-  if (int e = set_smem(linear_wgrad_tc_kernel, W_SMEM)) return e;
   const long long items = (long long)g.n_tiles * g.k_tiles;
-  linear_wgrad_tc_kernel<<<(int)(items < kSMs ? items : kSMs), W_THREADS, W_SMEM, st>>>(mdy, mx, dw, g);
+  const int grid = (int)(items < kSMs ? items : kSMs);
+  if (adam_pmv) {
+    if (int e = set_smem(linear_wgrad_tc_kernel<true>, W_SMEM)) return e;
+    linear_wgrad_tc_kernel<true><<<grid, WCfg<true>::THREADS, W_SMEM, st>>>(mdy, mx, dw, g);
+  } else {
+    if (int e = set_smem(linear_wgrad_tc_kernel<false>, W_SMEM)) return e;
+    linear_wgrad_tc_kernel<false><<<grid, WCfg<false>::THREADS, W_SMEM, st>>>(mdy, mx, dw, g);
+  }
   return check_launch("linear_wgrad_tc");
 }
 

@@ -63,7 +63,7 @@ def flat_layout(numels, align: int = _ALIGN):
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
                  shard_min_numel: int = 1 << 20, multicast: bool | None = None, broadcast_init: bool = True,
-                 overlap_backward: bool = False, fuse_into_backward: bool = False):
+                 overlap_backward: bool = False, fuse_into_backward: bool = False, defer_join: bool = True):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
@@ -76,6 +76,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat = None           # region dict of the flat bucket
         self._symm = None
         self._overlap = bool(overlap_backward)
+        self._defer_join = bool(defer_join)
         self._side = None           # stream of the updates launched from the backward pass
         self._written = set()       # ids of wide params whose gradient replica was written since the last step()
         self._launched = set()      # ... and whose update is already running on the side stream
@@ -312,11 +313,14 @@ class FusedAdam(torch.optim.Optimizer):
             # weight: each adopted parameter carries an event that ops.linear waits for in the next forward pass, so the tail
             # overlaps with the next step's conv forward instead of being exposed (N = 8: ~1 ms per step).  synchronize()
             # joins explicitly (checkpointing, evaluation code that reads the parameters directly).
-            ev = torch.cuda.Event()
-            ev.record(self._side)
-            for key in self._launched:
-                self._regions[key]["key"]._dd_ready_event = ev
-            self._pending = ev
+            if self._defer_join:
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+                for key in self._launched:
+                    self._regions[key]["key"]._dd_ready_event = ev
+                self._pending = ev
+            else:
+                torch.cuda.current_stream().wait_stream(self._side)
         self._launched.clear()
         self._written.clear()
         return loss
