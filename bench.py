@@ -586,10 +586,12 @@ def run_ours(args):
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         loss = step(resident)
     opt.synchronize()        # the last step's weight exchange may still be running on the optimizer's side stream: time it too
     e1.record()
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # host time to ENQUEUE a step (no device sync inside)
     barrier()
     launches = _lib.launch_count() - l0
     sec = e0.elapsed_time(e1) * 1e-3
@@ -669,7 +671,7 @@ def run_ours(args):
             "e2e": {"value": total / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3,
                     "note": "pinned host inputs copied every step on a side stream (double-buffered), loss read back"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_rows,
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_rows,
             "cpu_baseline": cpu, "final_loss": final_loss,
         }
         if wl.host_f32 is not None:

@@ -215,6 +215,131 @@ __global__ void __launch_bounds__(256) conv2d_wgrad_kernel(const T* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight gradient, second form: ALL taps per CTA.  The kernel above gives every (tap, pixel range) its own CTA, so the
+// pivot tensor P is re-read once per tap (49 x for the 7 x 7 layers) through scalar loads: 0.3-6 TFLOP/s on the
+// small-channel layers of the bounding-box model (up_conv_3 / 4, rm_conv_1, the strip convs, ss_conv), 150 of that
+// model's 174 ms step.  Here a CTA walks row segments of the pivot grid; a segment's P pixels and the KH rows of Q it
+// touches are staged in shared memory ONCE, and every thread owns a register tile acc[TT taps][TP cP][TQ cQ] that
+// lives for the whole launch (thread = (pixel lane, tap group, cP group, cQ group)).  Per-(CTA, pixel lane) partials,
+// folded in order by wgrad_fold_kernel (deterministic).
+// ------------------------------------------------------------------------------------------------
+struct WTile {
+  int ntg, npg, nqg, lanes;     // tap / cP / cQ groups, pixel lanes; ntg * npg * nqg * lanes <= 256
+  int seg, qw;                  // pivot pixels per row segment; staged Q pixels per row = (seg-1)*sw + (kw-1)*dw + 1
+  int segs_per_row, nseg;       // segments per pivot row; total segments = B * Hp * segs_per_row
+};
+
+template <typename T, int TT, int TP, int TQ>
+__global__ void __launch_bounds__(256) conv2d_wgrad_tile_kernel(const T* __restrict__ P, const T* __restrict__ Q,
+                                                                float* __restrict__ partial, WGeo g, WTile c) {
+  extern __shared__ float s_tile[];
+  const int cPp = c.npg * TP, cQp = c.nqg * TQ;
+  float* s_p = s_tile;                                  // [seg][cPp]
+  float* s_q = s_tile + c.seg * cPp;                    // [kh][qw][cQp]
+  const int tid = threadIdx.x;
+  const int ngroups = c.ntg * c.npg * c.nqg;
+  const int grp = tid % ngroups, pl = tid / ngroups;
+  const int qg = grp % c.nqg, pg = (grp / c.nqg) % c.npg, tg = grp / (c.nqg * c.npg);
+  const bool active = pl < c.lanes;
+  const int taps = g.kh * g.kw;
+  int qoff[TT];
+#pragma unroll
+  for (int tt = 0; tt < TT; ++tt) {
+    const int tap = min(tg * TT + tt, taps - 1);        // (padding taps recompute the last one; never written out)
+    qoff[tt] = ((tap / g.kw) * c.qw + (tap % g.kw) * g.dw) * cQp + qg * TQ;
+  }
+  float acc[TT][TP][TQ];
+#pragma unroll
+  for (int tt = 0; tt < TT; ++tt)
+#pragma unroll
+    for (int a = 0; a < TP; ++a)
+#pragma unroll
+      for (int b = 0; b < TQ; ++b) acc[tt][a][b] = 0.f;
+
+  for (int sgi = blockIdx.x; sgi < c.nseg; sgi += gridDim.x) {
+    const int ws = sgi % c.segs_per_row;
+    const int hp = (sgi / c.segs_per_row) % g.Hp;
+    const int b = sgi / (c.segs_per_row * g.Hp);
+    const int wp0 = ws * c.seg;
+    __syncthreads();
+    for (int e = tid; e < c.seg * cPp; e += 256) {
+      const int ch = e % cPp, px = e / cPp;
+      s_p[e] = (wp0 + px < g.Wp && ch < g.cP) ? dd::ld<T>(P + (((size_t)b * g.Hp + hp) * g.Wp + wp0 + px) * g.cP + ch) : 0.f;
+    }
+    const int wq0 = wp0 * g.sw - g.pw;
+    for (int e = tid; e < g.kh * c.qw * cQp; e += 256) {
+      const int ch = e % cQp, x = (e / cQp) % c.qw, khi = e / (cQp * c.qw);
+      const int hq = hp * g.sh - g.ph + khi * g.dh, wq = wq0 + x;
+      s_q[e] = (ch < g.cQ && hq >= 0 && hq < g.Hq && wq >= 0 && wq < g.Wq)
+                   ? dd::ld<T>(Q + (((size_t)b * g.Hq + hq) * g.Wq + wq) * g.cQ + ch) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      for (int px = pl; px < c.seg; px += c.lanes) {
+        float pv[TP];
+#pragma unroll
+        for (int a = 0; a < TP; ++a) pv[a] = s_p[px * cPp + pg * TP + a];
+        const float* qrow = s_q + px * g.sw * cQp;
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) {
+          float qv[TQ];
+#pragma unroll
+          for (int bq = 0; bq < TQ; ++bq) qv[bq] = qrow[qoff[tt] + bq];
+#pragma unroll
+          for (int a = 0; a < TP; ++a)
+#pragma unroll
+            for (int bq = 0; bq < TQ; ++bq) acc[tt][a][bq] = fmaf(pv[a], qv[bq], acc[tt][a][bq]);
+        }
+      }
+    }
+  }
+  if (active) {
+    float* out = partial + ((size_t)blockIdx.x * c.lanes + pl) * taps * g.cP * g.cQ;
+#pragma unroll
+    for (int tt = 0; tt < TT; ++tt) {
+      const int tap = tg * TT + tt;
+      if (tap >= taps) continue;
+#pragma unroll
+      for (int a = 0; a < TP; ++a)
+#pragma unroll
+        for (int bq = 0; bq < TQ; ++bq) {
+          const int cp = pg * TP + a, cq = qg * TQ + bq;
+          if (cp < g.cP && cq < g.cQ) out[((size_t)tap * g.cP + cp) * g.cQ + cq] = acc[tt][a][bq];
+        }
+    }
+  }
+}
+
+// picks a register tiling for the all-taps form; false: this layer keeps the per-tap kernel
+static bool wtile_config(const WGeo& g, int taps, int& TT, int& TP, int& TQ, WTile& c, size_t& smem, int& grid) {
+  if (g.cP % 4 != 0 && g.cP > 4) return false;
+  TP = 4;
+  TQ = g.cQ % 4 == 0 ? 4 : (g.cQ == 3 ? 3 : (g.cQ == 1 ? 1 : 0));
+  if (TQ == 0) return false;
+  TT = taps % 7 == 0 ? 7 : (taps <= 4 ? 4 : (taps % 8 == 0 ? 8 : 7));
+  if (TQ == 4 && TT == 8 && false) return false;
+  c.ntg = (taps + TT - 1) / TT; c.npg = (g.cP + TP - 1) / TP; c.nqg = (g.cQ + TQ - 1) / TQ;
+  const int ngroups = c.ntg * c.npg * c.nqg;
+  if (ngroups > 256) return false;
+  c.lanes = 256 / ngroups;
+  c.seg = 64;
+  while (true) {
+    c.qw = (c.seg - 1) * g.sw + (g.kw - 1) * g.dw + 1;
+    smem = ((size_t)c.seg * c.npg * TP + (size_t)g.kh * c.qw * c.nqg * TQ) * sizeof(float);
+    if (smem <= 96 * 1024 || c.seg <= 16) break;
+    c.seg /= 2;
+  }
+  if (smem > 200 * 1024) return false;
+  if (c.lanes > c.seg) c.lanes = c.seg;
+  c.segs_per_row = (g.Wp + c.seg - 1) / c.seg;
+  const long long nseg = (long long)g.B * g.Hp * c.segs_per_row;
+  if (nseg > 0x7fffffff) return false;
+  c.nseg = (int)nseg;
+  grid = (int)(nseg < 2 * dd::kSMs ? nseg : 2 * dd::kSMs);
+  return true;
+}
+
 // dw[cP][cQ][t] = sum over splits (in order) of partial[split][t][cP][cQ]
 __global__ void wgrad_fold_kernel(const float* __restrict__ partial, float* __restrict__ dw, int taps, int cPQ, int splits) {
   const int n = taps * cPQ;
@@ -286,6 +411,26 @@ int launch_gather(const T* x, const float* wg, const float* bias, const T* mask,
 }
 
 template <typename T>
+int launch_wgrad_tile(const T* P, const T* Q, float* partial, const WGeo& g, int taps, int& slots, cudaStream_t st) {
+  int TT, TP, TQ, grid;
+  WTile c;
+  size_t smem;
+  if (!wtile_config(g, taps, TT, TP, TQ, c, smem, grid)) return -1000;
+  slots = grid * c.lanes;
+#define DD_WT(a, b, q)                                                                                             \
+  if (TT == a && TP == b && TQ == q) {                                                                             \
+    auto k = conv2d_wgrad_tile_kernel<T, a, b, q>;                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+    if (e != cudaSuccess) return dd::fail((int)e, "conv2d wgrad tile: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
+    k<<<grid, 256, smem, st>>>(P, Q, partial, g, c);                                                               \
+    return dd::check_launch("conv2d_wgrad_tile");                                                                  \
+  }
+  DD_WT(7, 4, 4) DD_WT(7, 4, 1) DD_WT(7, 4, 3) DD_WT(8, 4, 4) DD_WT(4, 4, 4) DD_WT(4, 4, 1) DD_WT(8, 4, 3) DD_WT(8, 4, 1)
+#undef DD_WT
+  return -1000;
+}
+
+template <typename T>
 int launch_wgrad(const T* P, const T* Q, float* partial, const WGeo& g, int taps, int splits, cudaStream_t st) {
   dim3 grid(taps, splits);
   const int tp = (g.cP + 15) / 16, tq = (g.cQ + 15) / 16;
@@ -342,7 +487,8 @@ extern "C" size_t dd_conv2d_workspace_bytes(const dd_conv_desc* d) {
   const long long pivot = d->transposed ? np_in : np_out;
   const size_t partial = (size_t)wgrad_splits(d, pivot) * d->kh * d->kw * d->Cin * d->Cout * sizeof(float);
   const size_t chan = (size_t)kChanBlocks * d->Cout * sizeof(double) + 8;
-  const size_t a = wg_bytes(d), b = partial + chan;
+  const size_t tile_partial = (size_t)2 * dd::kSMs * 256 * 128 * sizeof(float);   // all-taps form: slots x taps x cP x cQ <= CTAs x 256 threads x 128 accumulators
+  const size_t a = wg_bytes(d), b = (partial > tile_partial ? partial : tile_partial) + chan;
   const size_t c = tc_wgrad_ok(d, DD_BF16) ? dd::conv_dil_wgrad_tc_ws_bytes(d->Cin, d->Cout, d->kh) + chan : 0;
   const size_t m = a > b ? a : b;
   return (m > c ? m : c) + 256;
@@ -448,16 +594,22 @@ extern "C" int dd_conv2d_wgrad(const void* x, const void* dy, float* dw, float* 
   if (!d->transposed) { g.cP = d->Cout; g.cQ = d->Cin; g.Hp = d->Ho; g.Wp = d->Wo; g.Hq = d->Hi; g.Wq = d->Wi; Pp = dy; Qp = x; }
   else { g.cP = d->Cin; g.cQ = d->Cout; g.Hp = d->Hi; g.Wp = d->Wi; g.Hq = d->Ho; g.Wq = d->Wo; Pp = x; Qp = dy; }
   float* partial = (float*)workspace;
-  int e;
-  if (dtype == DD_F32) e = launch_wgrad<float>((const float*)Pp, (const float*)Qp, partial, g, taps, splits, st);
-  else if (dtype == DD_BF16) e = launch_wgrad<__nv_bfloat16>((const __nv_bfloat16*)Pp, (const __nv_bfloat16*)Qp, partial, g, taps, splits, st);
-  else return dd::fail(DD_ERR_UNSUPPORTED, "dd_conv2d_wgrad: dtype %d", dtype);
+  int e, slots = splits;
+  if (dtype != DD_F32 && dtype != DD_BF16) return dd::fail(DD_ERR_UNSUPPORTED, "dd_conv2d_wgrad: dtype %d", dtype);
+  // the all-taps register-tiled form where a tiling exists (small channel counts); else one CTA per (tap, pixel range)
+  e = dtype == DD_F32 ? launch_wgrad_tile<float>((const float*)Pp, (const float*)Qp, partial, g, taps, slots, st)
+                      : launch_wgrad_tile<__nv_bfloat16>((const __nv_bfloat16*)Pp, (const __nv_bfloat16*)Qp, partial, g, taps, slots, st);
+  if (e == -1000) {
+    slots = splits;
+    e = dtype == DD_F32 ? launch_wgrad<float>((const float*)Pp, (const float*)Qp, partial, g, taps, splits, st)
+                        : launch_wgrad<__nv_bfloat16>((const __nv_bfloat16*)Pp, (const __nv_bfloat16*)Qp, partial, g, taps, splits, st);
+  }
   if (e) return e;
   const int n = taps * d->Cin * d->Cout;
-  wgrad_fold_kernel<<<(n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184, 256, 0, st>>>(partial, dw, taps, d->Cin * d->Cout, splits);
+  wgrad_fold_kernel<<<(n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184, 256, 0, st>>>(partial, dw, taps, d->Cin * d->Cout, slots);
   if (int e2 = dd::check_launch("conv2d_wgrad_fold")) return e2;
   if (db) {
-    double* cpart = reinterpret_cast<double*>(((uintptr_t)(partial + (size_t)splits * n) + 7) & ~(uintptr_t)7);
+    double* cpart = reinterpret_cast<double*>(((uintptr_t)(partial + (size_t)slots * n) + 7) & ~(uintptr_t)7);
     const int lanes = 256 / d->Cout > 0 ? 256 / d->Cout : 1;
     const long long want = (np_out + lanes - 1) / lanes;
     const int nblk = (int)(want < kChanBlocks ? want : kChanBlocks);
