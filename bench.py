@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-defer-join", action="store_true", help="A/B: join the overlapped weight exchange inside step()")
+    ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"],
+                    help="A/B: NVLink multicast (multimem) vs peer loads in the sharded update; auto = peer loads")
     a = ap.parse_args()
     if a.mode == "inference":
         a.config = "inference"
@@ -560,7 +562,8 @@ def run_ours(args):
     # world 1: one fused launch per tensor; world N: the wide FC weights are reduced, updated and all-gathered by ONE kernel
     # over NVLink peer memory (optim.FusedAdam / csrc/adam.cu), launched from the backward pass; the small tensors share
     # one flat sharded bucket
-    opt = FusedAdam(params, lr=1e-3, overlap_backward=True, defer_join=not args.no_defer_join)
+    opt = FusedAdam(params, lr=1e-3, overlap_backward=True, defer_join=not args.no_defer_join,
+                    multicast={"auto": None, "on": True, "off": False}[args.multicast])
     resident = [t.to(dev, non_blocking=True) for t in wl.host]
 
     def step(tensors):

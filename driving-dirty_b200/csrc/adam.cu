@@ -51,8 +51,12 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
 // MODE 0: local (grad / param = one pointer each).  MODE 1: peer pointers.  MODE 2: multicast pointers.
 // UNROLL independent 16-byte granules per thread and iteration: all their loads are issued before the first use, so that
 // enough bytes are in flight to cover the NVLink round trip with one resident CTA per SM.
+// 80 registers: the register file is split over the SM's four sub-partitions (16 K each).  Two update warps per sub-partition
+// take 2 x 2560; the input-gradient conv kernel that must run beside the update puts 4 of its 13 warps (88 registers) on one
+// sub-partition, 11264 -- together exactly 16 K.  With 96 registers here that kernel queued behind the whole update
+// (1.8 ms hole in the N = 2 multicast timeline, profiles/r2_step_timeline_n2_multicast_96regs.txt).
 template <int MODE, int UNROLL>
-__global__ void __maxnreg__(96) adam_kernel(PeerPtrs pp, const float* __restrict__ mc_grad, float* __restrict__ mc_param,
+__global__ void __maxnreg__(80) adam_kernel(PeerPtrs pp, const float* __restrict__ mc_grad, float* __restrict__ mc_param,
                                                         float* __restrict__ m, float* __restrict__ v, long long off,
                                                         long long n, int world, int rank, AdamHyper h) {
   // element i of the shard is element off + i of the full tensors; n and off are multiples of 4

@@ -226,6 +226,7 @@ int launch_s2_fwd(const void* in, const float* w, const float* bias, void* out, 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int items = B * ((Wo + TILE_M - 1) / TILE_M) * ((Ho + ROWS - 1) / ROWS);
   cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_s2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM);
+  cudaFuncSetAttribute(conv3x3_c32_s2_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return dd::fail((int)e, "conv_tc s2: cudaFuncSetAttribute(%d): %s", S2_SMEM, cudaGetErrorString(e));
   CUtensorMap m2, m1;
   int r = dd::tma_map_nhwc_sw64(&m2, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, 255, 2);      // 255 source pixels -> 128 loaded
@@ -519,6 +520,7 @@ int launch_s1(const void* in, const float* w, const float* bias, const void* mas
   const int items = B * ((W + TILE_M - 1) / TILE_M) * ((H + S1_ROWS - 1) / S1_ROWS);
   auto k = conv3x3_c32_s1_tc_kernel<MODE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_SMEM);
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return dd::fail((int)e, "conv_tc s1: cudaFuncSetAttribute(%d): %s", S1_SMEM, cudaGetErrorString(e));
   const int grid = items < dd::kSMs ? items : dd::kSMs;
   if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return dd::fail(DD_ERR_ALIGNMENT, "conv_tc s1: input is not 16-byte aligned");
@@ -940,6 +942,7 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const int items = B * (((W + 1) / 2 + TILE_M - 1) / TILE_M) * (((H + 1) / 2 + DG_MROWS - 1) / DG_MROWS);
     cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_dgrad_s2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
+    cudaFuncSetAttribute(conv3x3_c32_dgrad_s2_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail((int)e, "dgrad_s2_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return fail(DD_ERR_ALIGNMENT, "dgrad_s2_tc: dy is not 16-byte aligned");
     CUtensorMap mdy;
@@ -960,6 +963,7 @@ int conv_c1_fwd_tc(const void* in, int in_flags, const float* w, const float* bi
   const int grid = items < kSMs ? items : kSMs;
   auto launch1 = [&](auto k, auto* typed_in) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail((int)e, "conv_c1_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     k<<<grid, C1_THREADS, C1_SMEM, st>>>(typed_in, w, bias, (__nv_bfloat16*)out, B, H, Wm);
     return check_launch("conv_c1_tc");

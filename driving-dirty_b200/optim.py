@@ -106,10 +106,11 @@ class FusedAdam(torch.optim.Optimizer):
         grp = self.group if self.group is not None else dist.group.WORLD
         hdl = symm_mem.rendezvous(buf, grp)
         # per NVLink direction and GPU the multicast form moves n(1 + 1/N) bytes (the switch also loops the own replica
-        # back), peer loads / stores 2n(N-1)/N, at a somewhat lower achieved link rate for multimem.  Measured per step
-        # (profiles/r1_step_times_n8.txt and the N = 2 / N = 4 runs): N = 2: 3.5 vs 2.1 ms for the update alone;
-        # N = 4: 8.56 vs 7.9-8.2 ms per training step; N = 8: 8.68 vs 8.8 ms.  Multicast from N = 6 on.
-        want_mc = (self.world >= 6) if multicast is None else bool(multicast)
+        # back), peer loads / stores 2n(N-1)/N.  Alone, the multicast update is the shorter kernel from N = 6 on (2.0 vs
+        # 3.0 ms at N = 8), but it runs BESIDE the conv backward pass, and multimem traffic slows those HBM-bound kernels far
+        # more than peer loads do (N = 8, profiles/r2_step_timeline_n8_*.txt: input-gradient conv 1.36 vs 0.82 ms, c3
+        # weight gradient 0.69 vs 0.28): 6.68 vs 6.46 ms per step at N = 8, 6.24 vs 5.66 at N = 2.  Peer loads by default.
+        want_mc = False if multicast is None else bool(multicast)
         mc = int(hdl.multicast_ptr) if (want_mc and hdl.has_multicast_support) else 0
         if multicast is True and mc == 0:
             raise RuntimeError("FusedAdam: multicast requested but the symmetric buffer has no multicast mapping")

@@ -14,7 +14,9 @@ from driving_dirty_b200.optim import FusedAdam
 from driving_dirty_b200.synthetic import scene_batch
 model = bench.build_model("bf16", dev)
 params = [p for p in model.parameters() if p.requires_grad]
-opt = FusedAdam(params, lr=1e-3, overlap_backward=os.environ.get("OVERLAP", "1") == "1")
+mc = os.environ.get("MC")
+opt = FusedAdam(params, lr=1e-3, overlap_backward=os.environ.get("OVERLAP", "1") == "1",
+                multicast=None if mc is None else mc == "1")
 views, road = scene_batch(32, 256, 306, seed=1 + rank)
 views, road = views.to(dev), road.to(dev)
 def step():
