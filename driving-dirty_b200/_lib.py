@@ -36,6 +36,7 @@ SIGNATURES = {
     "dd_conv3x3_c32_wgrad": (_I, [_P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _P]),
     "dd_conv_wgrad_workspace_bytes": (_Z, []),
     "dd_pool4_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "dd_pool4_fwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "dd_pool4_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "dd_nhwc_to_nchw_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "dd_nchw_f32_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

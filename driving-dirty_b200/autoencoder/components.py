@@ -88,6 +88,9 @@ class Encoder(nn.Module):
         return (32 * h3 * w3) // pooling_size
 
     def _tail(self, feats):
+        # bf16 activations: fc1 streams its weight through the tensor cores (tf32), whether the pooled features arrive as
+        # bf16 (training) or as the fp32 copy of the same values (inference); owners may change compute_dtype after __init__
+        self.fc1.allow_tf32 = self.compute_dtype == torch.bfloat16
         x = self.fc1(feats)
         x = self.fc2(x)
         return ops.linear(x, self.fc_z_out.weight, self.fc_z_out.bias, self.impl)

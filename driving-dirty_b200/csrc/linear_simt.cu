@@ -411,8 +411,9 @@ extern "C" int dd_linear_fwd(const void* x, int x_dtype, const float* w, const f
              "dd_linear_fwd: tcgen05 path needs fp32 x, N %% 4 == K %% 4 == 0 and N*K >= 2^22 (B=%d N=%d K=%lld)", B, N, K);
   cudaStream_t st = dd::as_stream(stream);
   const size_t esz = x_dtype == DD_F32 ? 4 : 2;
-  for (int b0 = 0; b0 < B; b0 += 32) {
-    const int bc = B - b0 < 32 ? B - b0 : 32;
+  const int rows_per_pass = use_tc(impl, B, N, K) ? 256 : 32;      // the tcgen05 forward takes up to 256 rows per weight pass
+  for (int b0 = 0; b0 < B; b0 += rows_per_pass) {
+    const int bc = B - b0 < rows_per_pass ? B - b0 : rows_per_pass;
     const char* xp = (const char*)x + (size_t)b0 * K * esz;
     float* yp = y + (size_t)b0 * N;
     int e;

@@ -24,6 +24,7 @@
 namespace {
 
 constexpr int NB = 32;                    // batch rows per launch (MMA N, or K for wgrad)
+constexpr int kLinearTcMaxRows = 256;     // forward only: rows per pass (SCfg below)
 constexpr int THREADS = 192;
 constexpr int BOX = 32 * 128;             // a 32-row x 128-byte TMA box
 constexpr int kChunk = 32;                // contraction elements per stage (one 128-byte swizzle span)
@@ -42,12 +43,18 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 // ------------------------------------------------------------------------------------------------
 // fwd (MODE 0) and dgrad (MODE 1): out[b * LD + r] = sum over the contraction, r = row of the 128-row tile
 // ------------------------------------------------------------------------------------------------
-constexpr int S_STAGES = 8;
-constexpr int S_STAGE_BYTES = 4 * BOX + BOX;      // A: 128 x 128 B (fwd) or 4 boxes (dgrad); B: one box
-constexpr int S_SMEM = S_STAGES * S_STAGE_BYTES + 2048;
+// NBT = batch rows per pass (the MMA N): 32 for the training step; the inference front end sends up to 256 scenes per
+// call, and with NBT = 256 the weights still cross HBM once (they were re-read for every 32 rows: 8 passes over the
+// 0.96 GB of Encoder.fc1 at batch 256)
+template <int NBT> struct SCfg {
+  static constexpr int STAGES = NBT <= 32 ? 8 : NBT <= 64 ? 8 : NBT <= 128 ? 6 : 4;
+  static constexpr int STAGE_BYTES = 4 * BOX + NBT * 128;      // A: 128 x 128 B (fwd) or 4 boxes (dgrad); B: NBT rows x 128 B
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 2048;
+};
+constexpr int S_MAX_STAGES = 8;
 
 struct StreamBars {
-  uint64_t full[S_STAGES], empty[S_STAGES], acc_full[2], acc_empty[2];
+  uint64_t full[S_MAX_STAGES], empty[S_MAX_STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
@@ -57,12 +64,13 @@ struct StreamGeo {
   int chunks, chunks_per_split;
 };
 
-template <int MODE, typename TOUT>
+template <int MODE, typename TOUT, int NBT = NB>
 __global__ void __launch_bounds__(THREADS, 1) linear_stream_tc_kernel(const __grid_constant__ CUtensorMap map_w,
                                                                        const __grid_constant__ CUtensorMap map_v,
                                                                        const float* __restrict__ bias,
                                                                        TOUT* __restrict__ out, float* __restrict__ partial,
                                                                        StreamGeo g) {
+  constexpr int S_STAGES = SCfg<NBT>::STAGES, S_STAGE_BYTES = SCfg<NBT>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   StreamBars* bars = reinterpret_cast<StreamBars*>(smem + S_STAGES * S_STAGE_BYTES);
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_stream_tc_kernel(const __gr
     umma::tma_prefetch_desc(&map_w);
     umma::tma_prefetch_desc(&map_v);
   }
-  if (warp == 1) umma::tmem_alloc(&bars->tmem_base, 2 * NB);
+  if (warp == 1) umma::tmem_alloc(&bars->tmem_base, 2 * NBT);
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_stream_tc_kernel(const __gr
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =======================================================
-    constexpr uint32_t idesc = umma::make_idesc_tf32(128, NB, MODE == 1, false);
+    constexpr uint32_t idesc = umma::make_idesc_tf32(128, NBT, MODE == 1, false);
     uint32_t c = 0, n_item = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n_item) {
       const int si = it / g.tiles;
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_stream_tc_kernel(const __gr
             uint32_t a_lo, a_hi;
             if (MODE == 0) { a_lo = umma::desc_lo(base + k * 32, 16); a_hi = umma::desc_hi_sw128(1024); }
             else { a_lo = umma::desc_lo(base + k * 1024, BOX); a_hi = umma::desc_hi_sw128_base32(512); }
-            umma::mma_tf32_lohi(tmem + a * NB, a_lo, a_hi, umma::desc_lo(base + 4 * BOX + k * 32, 16), umma::desc_hi_sw128(1024),
+            umma::mma_tf32_lohi(tmem + a * NBT, a_lo, a_hi, umma::desc_lo(base + 4 * BOX + k * 32, 16), umma::desc_hi_sw128(1024),
                                 idesc, (ch > c0 || k > 0) ? 1u : 0u);
           }
           umma::mma_commit(&bars->empty[s]);
@@ -147,31 +155,38 @@ __global__ void __launch_bounds__(THREADS, 1) linear_stream_tc_kernel(const __gr
       const uint32_t a = n_item & 1;
       mbar_wait_relaxed(&bars->acc_full[a], (n_item >> 1) & 1);
       umma::tc_fence_after_sync();
-      uint32_t v[32];
-      umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + a * NB, v);
-      umma::tmem_ld_wait();
-      umma::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&bars->acc_empty[a]);
       const int r = ti * 128 + quarter * 32 + lane;
-      if (r < g.LD) {
-        if (g.splits == 1) {
-          const float bv = bias ? __ldg(bias + r) : 0.f;
-#pragma unroll
-          for (int b = 0; b < NB; ++b)
-            if (b < g.B) dd::st<TOUT>(out + (size_t)b * g.LD + r, __uint_as_float(v[b]) + bv);
-        } else {
-          float* p = partial + (size_t)si * g.B * g.LD + r;
-#pragma unroll
-          for (int b = 0; b < NB; ++b)
-            if (b < g.B) p[(size_t)b * g.LD] = __uint_as_float(v[b]);
+      const float bv = (g.splits == 1 && bias && r < g.LD) ? __ldg(bias + r) : 0.f;
+#pragma unroll 1
+      for (int nb = 0; nb < NBT; nb += 32) {
+        uint32_t v[32];
+        umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + a * NBT + nb, v);
+        umma::tmem_ld_wait();
+        const bool last = nb + 32 >= NBT || nb + 32 >= g.B;
+        if (last) {                                      // last group read: hand the accumulator back before the stores
+          umma::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(&bars->acc_empty[a]);
         }
+        if (r < g.LD) {
+          if (g.splits == 1) {
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+              if (nb + b < g.B) dd::st<TOUT>(out + (size_t)(nb + b) * g.LD + r, __uint_as_float(v[b]) + bv);
+          } else {
+            float* p = partial + (size_t)si * g.B * g.LD + (size_t)nb * g.LD + r;
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+              if (nb + b < g.B) p[(size_t)b * g.LD] = __uint_as_float(v[b]);
+          }
+        }
+        if (last) break;
       }
     }
   }
   umma::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem, 2 * NB);
+  if (warp == 1) umma::tmem_dealloc(tmem, 2 * NBT);
 }
 
 // out[i] = sum over splits (in order) of partial[s][i] (+ bias[i % LD])
@@ -412,18 +427,30 @@ bool linear_tc_supported(int B, int N, long long K) {
 }
 
 size_t linear_tc_workspace_bytes(int B, int N, long long K) {
-  const int Bc = B < NB ? B : NB;
+  const int Bf = B < kLinearTcMaxRows ? B : kLinearTcMaxRows;     // forward: up to 256 rows per pass
+  const int Bd = B < NB ? B : NB;                                 // input gradient: 32
   int s1, c1, s2, c2;
   plan_stream(ceil_div_ll(N, 128), ceil_div_ll(K, kChunk), s1, c1);      // fwd: tiles over N, contraction K
   plan_stream(ceil_div_ll(K, 128), ceil_div_ll(N, kChunk), s2, c2);      // dgrad: tiles over K, contraction N
-  const size_t a = s1 > 1 ? (size_t)s1 * Bc * N * sizeof(float) : 0;
-  const size_t b = s2 > 1 ? (size_t)s2 * Bc * K * sizeof(float) : 0;
+  const size_t a = s1 > 1 ? (size_t)s1 * Bf * N * sizeof(float) : 0;
+  const size_t b = s2 > 1 ? (size_t)s2 * Bd * K * sizeof(float) : 0;
   return (a > b ? a : b) + 256;
 }
 
-// x fp32 [B][K] (B <= 32), W fp32 [N][K], y fp32 [B][N]
+template <int NBT>
+int launch_fwd(const CUtensorMap& mw, const CUtensorMap& mx, const float* bias, float* y, float* ws, const StreamGeo& g,
+               cudaStream_t st) {
+  auto k = linear_stream_tc_kernel<0, float, NBT>;
+  if (int e = set_smem(k, SCfg<NBT>::SMEM)) return e;
+  const int items = g.tiles * g.splits;
+  k<<<items < kSMs ? items : kSMs, THREADS, SCfg<NBT>::SMEM, st>>>(mw, mx, bias, y, ws, g);
+  return check_launch("linear_fwd_tc");
+}
+
+// x fp32 [B][K] (B <= 256: one pass over the weights), W fp32 [N][K], y fp32 [B][N]
 int linear_fwd_tc(const float* x, const float* w, const float* bias, float* y, void* ws, size_t ws_bytes, int B, int N,
                   long long K, cudaStream_t st) {
+  if (B > kLinearTcMaxRows) return fail(DD_ERR_UNSUPPORTED, "linear_fwd_tc: %d rows per pass (max %d)", B, kLinearTcMaxRows);
   StreamGeo g;
   g.B = B; g.LD = N;
   g.tiles = ceil_div_ll(N, 128);
@@ -431,16 +458,17 @@ int linear_fwd_tc(const float* x, const float* w, const float* bias, float* y, v
   plan_stream(g.tiles, g.chunks, g.splits, g.chunks_per_split);
   if (g.splits > 1 && ws_bytes < (size_t)g.splits * B * N * sizeof(float))
     return fail(DD_ERR_WORKSPACE, "linear_fwd_tc: workspace %zu too small for %d splits", ws_bytes, g.splits);
+  const int nbt = B <= 32 ? 32 : B <= 64 ? 64 : B <= 128 ? 128 : 256;
   CUtensorMap mw, mx;
   char msg[256];
   if (tma_map_2d_checked(&mw, w, 4, N, K, K, 32, 128, false, msg, sizeof msg) ||
-      tma_map_2d_checked(&mx, x, 4, B, K, K, 32, 32, false, msg, sizeof msg))
+      tma_map_2d_checked(&mx, x, 4, B, K, K, 32, nbt, false, msg, sizeof msg))
     return fail(DD_ERR_UNSUPPORTED, "linear_fwd_tc: %s", msg);
-  auto k = linear_stream_tc_kernel<0, float>;
-  if (int e = set_smem(k, S_SMEM)) return e;
-  const int items = g.tiles * g.splits;
-  k<<<items < kSMs ? items : kSMs, THREADS, S_SMEM, st>>>(mw, mx, bias, y, (float*)ws, g);
-  if (int e = check_launch("linear_fwd_tc")) return e;
+  int e = nbt == 32 ? launch_fwd<32>(mw, mx, bias, y, (float*)ws, g, st)
+        : nbt == 64 ? launch_fwd<64>(mw, mx, bias, y, (float*)ws, g, st)
+        : nbt == 128 ? launch_fwd<128>(mw, mx, bias, y, (float*)ws, g, st)
+                     : launch_fwd<256>(mw, mx, bias, y, (float*)ws, g, st);
+  if (e) return e;
   if (g.splits > 1) {
     const long long n = (long long)B * N;
     split_fold_kernel<float><<<ceil_div_ll(n, 256), 256, 0, st>>>((const float*)ws, bias, y, g.splits, n, N);
@@ -469,14 +497,14 @@ int linear_dgrad_tc(const float* dy, const float* w, void* dx, int dx_dtype, voi
   const long long n = (long long)B * K;
   if (dx_dtype == DD_F32) {
     auto k = linear_stream_tc_kernel<1, float>;
-    if (int e = set_smem(k, S_SMEM)) return e;
-    k<<<grid, THREADS, S_SMEM, st>>>(mw, mdy, nullptr, (float*)dx, (float*)ws, g);
+    if (int e = set_smem(k, SCfg<NB>::SMEM)) return e;
+    k<<<grid, THREADS, SCfg<NB>::SMEM, st>>>(mw, mdy, nullptr, (float*)dx, (float*)ws, g);
     if (int e = check_launch("linear_dgrad_tc")) return e;
     if (g.splits > 1) split_fold_kernel<float><<<ceil_div_ll(n, 256), 256, 0, st>>>((const float*)ws, nullptr, (float*)dx, g.splits, n, (int)K);
   } else {
     auto k = linear_stream_tc_kernel<1, __nv_bfloat16>;
-    if (int e = set_smem(k, S_SMEM)) return e;
-    k<<<grid, THREADS, S_SMEM, st>>>(mw, mdy, nullptr, (__nv_bfloat16*)dx, (float*)ws, g);
+    if (int e = set_smem(k, SCfg<NB>::SMEM)) return e;
+    k<<<grid, THREADS, SCfg<NB>::SMEM, st>>>(mw, mdy, nullptr, (__nv_bfloat16*)dx, (float*)ws, g);
     if (int e = check_launch("linear_dgrad_tc")) return e;
     if (g.splits > 1)
       split_fold_kernel<__nv_bfloat16><<<ceil_div_ll(n, 256), 256, 0, st>>>((const float*)ws, nullptr, (__nv_bfloat16*)dx, g.splits, n, (int)K);

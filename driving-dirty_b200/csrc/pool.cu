@@ -25,8 +25,8 @@ __device__ __forceinline__ void load_tile(const T* __restrict__ img, long long p
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) pool4_fwd_tiled(const T* __restrict__ a3, T* __restrict__ pooled, int HW) {
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) pool4_fwd_tiled(const T* __restrict__ a3, TO* __restrict__ pooled, int HW) {
   __shared__ float s[TP * PAD];
   __shared__ float so[C * PAD];
   const int tid = threadIdx.x, b = blockIdx.y;
@@ -41,10 +41,10 @@ __global__ void __launch_bounds__(256) pool4_fwd_tiled(const T* __restrict__ a3,
   }
   __syncthreads();
   const int Q = HW / 4, nq = npix / 4;
-  T* out = pooled + (size_t)b * C * Q + p0 / 4;
+  TO* out = pooled + (size_t)b * C * Q + p0 / 4;
   for (int i = tid; i < C * (TP / 4); i += 256) {
     const int ql = i & 31, cc = i >> 5;
-    if (ql < nq) dd::st<T>(out + (size_t)cc * Q + ql, so[cc * PAD + ql]);
+    if (ql < nq) dd::st<TO>(out + (size_t)cc * Q + ql, so[cc * PAD + ql]);
   }
 }
 
@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(256) pool4_bwd_tiled(const T* __restrict__ a3,
 }
 
 // any H*W: one thread per window
-template <typename T, bool BWD>
-__global__ void pool4_generic(const T* __restrict__ a3, const T* __restrict__ dpooled, T* __restrict__ out, int HW,
+template <typename T, bool BWD, typename TO = T>
+__global__ void pool4_generic(const T* __restrict__ a3, const T* __restrict__ dpooled, TO* __restrict__ out, int HW,
                               long long windows_per_img, long long total) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -115,12 +115,12 @@ __global__ void pool4_generic(const T* __restrict__ a3, const T* __restrict__ dp
     for (int e = 1; e < 4; ++e)
       if (v[e] > mx) { mx = v[e]; m = e; }
     if (!BWD) {
-      dd::st<T>(out + idx, mx);
+      dd::st<TO>(out + idx, mx);
     } else {
       const float g = mx > 0.f ? dd::ld<T>(dpooled + idx) : 0.f;
-      T* o = out + (size_t)b * HW * C;
+      TO* o = out + (size_t)b * HW * C;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) dd::st<T>(o + off[e], e == m ? g : 0.f);
+      for (int e = 0; e < 4; ++e) dd::st<TO>(o + off[e], e == m ? g : 0.f);
     }
   }
 }
@@ -159,7 +159,7 @@ int pool_dispatch(const T* a3, const T* dpooled, T* out, int B, int H, int W, bo
   const int HW = H * W;
   if (HW % 4 == 0) {
     dim3 grid((HW + TP - 1) / TP, B);
-    if (!bwd) pool4_fwd_tiled<T><<<grid, 256, 0, st>>>(a3, out, HW);
+    if (!bwd) pool4_fwd_tiled<T, T><<<grid, 256, 0, st>>>(a3, out, HW);
     else pool4_bwd_tiled<T><<<grid, 256, 0, st>>>(a3, dpooled, out, HW);
   } else {
     const long long wpi = (long long)C * HW / 4, total = wpi * B;
@@ -168,7 +168,29 @@ int pool_dispatch(const T* a3, const T* dpooled, T* out, int B, int H, int W, bo
   }
   return dd::check_launch(bwd ? "pool4_bwd" : "pool4_fwd");
 }
+// forward with fp32 features out of a bf16 activation: the max of bf16 values is a bf16 value, so the fp32 features hold
+// exactly what the bf16 ones would, and the tf32 linear that follows reads them without a conversion pass
+int pool_fwd_bf16_to_f32(const __nv_bfloat16* a3, float* out, int B, int H, int W, cudaStream_t st) {
+  const int HW = H * W;
+  if (HW % 4 == 0) {
+    pool4_fwd_tiled<__nv_bfloat16, float><<<dim3((HW + TP - 1) / TP, B), 256, 0, st>>>(a3, out, HW);
+  } else {
+    const long long wpi = (long long)C * HW / 4, total = wpi * B;
+    pool4_generic<__nv_bfloat16, false, float><<<grid1d(total), 256, 0, st>>>(a3, nullptr, out, HW, wpi, total);
+  }
+  return dd::check_launch("pool4_fwd");
+}
 }  // namespace
+
+extern "C" int dd_pool4_fwd_f32(const void* a3, float* pooled, int dtype, int B, int H, int W, void* stream) {
+  DD_REQUIRE(a3 && pooled, DD_ERR_BAD_ARG, "dd_pool4_fwd_f32: null pointer");
+  DD_REQUIRE(B >= 0 && H > 0 && W > 0, DD_ERR_BAD_ARG, "dd_pool4_fwd_f32: bad shape");
+  if (B == 0) return 0;
+  cudaStream_t st = dd::as_stream(stream);
+  if (dtype == DD_F32) return pool_dispatch<float>((const float*)a3, nullptr, pooled, B, H, W, false, st);
+  if (dtype == DD_BF16) return pool_fwd_bf16_to_f32((const __nv_bfloat16*)a3, pooled, B, H, W, st);
+  return dd::fail(DD_ERR_UNSUPPORTED, "dd_pool4_fwd_f32: dtype %d", dtype);
+}
 
 extern "C" int dd_pool4_fwd(const void* a3, void* pooled, int dtype, int B, int H, int W, void* stream) {
   DD_REQUIRE(a3 && pooled, DD_ERR_BAD_ARG, "dd_pool4_fwd: null pointer");

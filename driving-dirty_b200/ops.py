@@ -162,6 +162,10 @@ class EncoderConvStack(torch.autograd.Function):
         elif c3_only:
             out = torch.empty(B, 32, H3, W3, dtype=torch.float32, device=dev)
             call("dd_nhwc_to_nchw_f32", a3.data_ptr(), code, out.data_ptr(), B, 32, H3, W3, st)
+        elif not any(ctx.needs_input_grad):
+            # inference: fp32 features (exactly the bf16 maxima) -- the tf32 linear that follows reads them as they are
+            out = torch.empty(B, 8 * H3 * W3, dtype=torch.float32, device=dev)
+            call("dd_pool4_fwd_f32", a3.data_ptr(), out.data_ptr(), code, B, H3, W3, st)
         else:
             out = torch.empty(B, 8 * H3 * W3, dtype=act_dtype, device=dev)
             call("dd_pool4_fwd", a3.data_ptr(), out.data_ptr(), code, B, H3, W3, st)

@@ -97,6 +97,9 @@ size_t dd_conv_wgrad_workspace_bytes(void);
  * a3 NHWC [B,H,W,32] -> pooled [B, (32*H*W)/4] in the reference's feature order.
  * bwd: da3 = scatter of dpooled to the FIRST max of each window, times (a3 > 0). */
 int dd_pool4_fwd(const void* a3, void* pooled, int dtype, int B, int H, int W, void* stream);
+/* same, the pooled features always fp32 (a bf16 a3's maxima are exact in fp32): what Encoder.fc1 (components.py:105) reads on
+ * the inference path, where no backward pass needs the bf16 copy */
+int dd_pool4_fwd_f32(const void* a3, float* pooled, int dtype, int B, int H, int W, void* stream);
 int dd_pool4_bwd(const void* a3, const void* dpooled, void* da3, int dtype, int B, int H, int W,
                  void* stream);
 

@@ -298,6 +298,9 @@ def test_pool4_fwd_bwd_exact(dd, dtype, B, H, W):
     pooled = torch.empty(B, n_out, dtype=dtype, device="cuda")
     call("dd_pool4_fwd", a3d.data_ptr(), pooled.data_ptr(), code, B, H, W, st)
     assert torch.equal(pooled.float().cpu(), ref)          # max of stored values: exact in any dtype
+    pooled32 = torch.empty(B, n_out, dtype=torch.float32, device="cuda")      # the inference path's fp32 features
+    call("dd_pool4_fwd_f32", a3d.data_ptr(), pooled32.data_ptr(), code, B, H, W, st)
+    assert torch.equal(pooled32.cpu(), ref)
     # backward: route to the FIRST max, times relu'(a3)
     a3r = a3.clone().requires_grad_(True)
     p = F.max_pool1d(F.relu(a3r).reshape(B, -1).unsqueeze(1), 4).squeeze(1)
@@ -373,6 +376,25 @@ def test_linear_tcgen05_fwd_dgrad_wgrad(dd, xdtype, B, N, K):
     xd2 = x.detach().to(xdtype).cuda().requires_grad_(True)
     yd2 = dd.linear(xd2, wd, bd, impl=2)
     assert torch.equal(yd2, yd)
+
+
+@pytest.mark.parametrize("B", [33, 64, 100, 128, 200, 256, 300])
+@pytest.mark.parametrize("N,K", [(256, 32768 + 96), (33000, 128), (1028, 4100)])
+def test_linear_tcgen05_fwd_wide_batch(dd, B, N, K):
+    """Inference batches: up to 256 rows share ONE pass over the weights (MMA N = 64 / 128 / 256); more are chunked by 256.
+    Same values as the 32-row passes of the training step to tf32 accuracy, deterministic."""
+    g = torch.Generator().manual_seed(67 + B)
+    x = torch.randn(B, K, generator=g)
+    w = (torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5
+    b = (torch.rand(N, generator=g) * 2 - 1) * 0.1
+    y = F.linear(x, w, b)
+    with torch.no_grad():
+        yd = dd.linear(x.cuda(), w.cuda(), b.cuda(), impl=2)
+        assert rel_max_err(yd, y) < TF32_TOL
+        assert torch.equal(dd.linear(x.cuda(), w.cuda(), b.cuda(), impl=2), yd)
+        # rows do not mix: any 32-row slice run on its own gives the same bits (same k order, same split plan per tile)
+        y32 = dd.linear(x[:32].cuda(), w.cuda(), b.cuda(), impl=2)
+        assert rel_max_err(yd[:32], y32) < 1e-6
 
 
 # ------------------------------------------------------------------------------- loss / TS ---
