@@ -517,6 +517,8 @@ int conv3x3_c32_wgrad_tc(const void* x, const void* dy, float* dw, float* db, vo
 bool conv_tc_supported(int H, int W, int stride, int mode);
 int conv_c1_fwd_tc(const void* in, int in_flags, const float* w, const float* bias, void* out, int B, int H, int Wm,
                    cudaStream_t st);
+int enc_c1c2_fused_fwd_tc(const void* in, int in_flags, const float* w1, const float* b1, const float* w2, const float* b2,
+                          void* out, int B, int H, int Wm, cudaStream_t st);
 int conv_c1_wgrad_tc(const void* in, int in_flags, const void* dy, float* dw, float* db, void* ws, size_t ws_bytes,
                      int B, int H, int Wm, cudaStream_t st);
 }  // namespace dd
@@ -584,6 +586,17 @@ extern "C" int dd_conv3x3_c32_wgrad(const void* x, const void* dy, float* dw, fl
     return conv_wgrad_simt<__nv_bfloat16>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, db,
                                           (float*)workspace, B, H, W, stride, st);
   return dd::fail(DD_ERR_UNSUPPORTED, "dd_conv3x3_c32_wgrad: dtype %d", dtype);
+}
+
+extern "C" int dd_encoder_c1c2_fused_fwd(const void* in_, int in_flags, const float* w1_oihw, const float* bias1,
+                                         const float* w2_oihw, const float* bias2, void* a2, int B, int H, int Wm,
+                                         void* stream) {
+  DD_REQUIRE(in_ && w1_oihw && bias1 && w2_oihw && bias2 && a2, DD_ERR_BAD_ARG, "dd_encoder_c1c2_fused_fwd: null pointer");
+  DD_REQUIRE(B >= 0 && H > 0 && Wm > 0, DD_ERR_BAD_ARG, "dd_encoder_c1c2_fused_fwd: bad shape");
+  DD_REQUIRE((in_flags & ~3) == 0, DD_ERR_BAD_ARG, "dd_encoder_c1c2_fused_fwd: in_flags %d", in_flags);
+  DD_REQUIRE(!(in_flags & DD_IN_VIEWS) || Wm % 6 == 0, DD_ERR_BAD_ARG, "dd_encoder_c1c2_fused_fwd: mosaic width %d not a multiple of 6", Wm);
+  if (B == 0) return 0;
+  return dd::enc_c1c2_fused_fwd_tc(in_, in_flags, w1_oihw, bias1, w2_oihw, bias2, a2, B, H, Wm, dd::as_stream(stream));
 }
 
 extern "C" int dd_conv_c1_fwd(const void* in_, int in_flags, const float* w_oihw, const float* bias, void* out,

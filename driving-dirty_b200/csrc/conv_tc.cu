@@ -22,6 +22,7 @@
 // full/empty (4 x 32 TMEM columns), so loads, MMAs and epilogues of different rows overlap.
 #include "dd_common.cuh"
 
+#include <cstdlib>
 #include "tma_host.h"
 #include "umma.cuh"
 
@@ -917,6 +918,311 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __
 }
 
 
+// ================================================================================================
+// Fused inference front of the encoder (components.py:41-43): relu(c1(x)) -> relu(c2(.)) in ONE kernel.
+// The first activation (963 MB per 32 scenes as bf16) never touches HBM: a CTA walks a strip of 126 output
+// pixels down 64 rows; per row
+//   converter warps   views / mosaic row (fp32 or raw bytes) -> [130 px][8 ch] bf16 plane      (as conv_c1_tc_kernel)
+//   MMA warp          c1: 6 MMAs (M=128, N=32) over three planes -> TMEM;  c2: row-scatter MMAs (as the s1 kernel) over
+//                     the a1 slab the first epilogue wrote, E_LAG rows behind
+//   epilogue 1        TMEM -> bias + ReLU -> bf16 -> shared memory, in the K-major SWIZZLE_64B layout the c2 MMAs read
+//                     ([130 px][32 ch], 64-byte rows, 16-byte chunk ^= (px >> 1) & 3); pixels / rows outside the image
+//                     are written as ZERO (c2's padding), not as relu(bias)
+//   epilogue 2        TMEM -> bias + ReLU -> bf16 -> a2 in HBM (bit-identical to the two-kernel path: a1 is rounded to
+//                     bf16 at the same point, the MMAs see the same operands in the same order)
+// Halo recompute: 128 a1 pixels per 126 outputs, 66 a1 rows per 64.  Hand-shakes: the MMA warp publishes ONE commit
+// per c1 batch (c1_done: accumulator full + oldest plane free) and ONE per c2 batch (c2_done: output row j-2 complete +
+// a1 slab free); ring indices are global row counters, two no-op commits per item keep c1_done in step with the planes.
+// ================================================================================================
+constexpr int E_STRIP = 126;
+constexpr int E_ROWS = 64;
+constexpr int E_NCONV = 6;                           // converter warps 0..5
+constexpr int E_MMA_WARP = E_NCONV;                  // warp 6 issues the c1 MMAs, warp 7 the c2 MMAs: every mbarrier wait and
+constexpr int E_MMA2_WARP = E_NCONV + 1;             // tcgen05.commit costs the issuing thread 100-200 cycles, and one thread
+                                                     // doing both batches' hand-shakes left the tensor pipe idle 60 % of the time
+constexpr int E_EPI1 = 8, E_EPI2 = 8;                // warps 8..15: a1 rows; warps 16..23: a2 rows (two warps per TMEM lane
+                                                     // quarter each, alternating rows)
+constexpr int E_THREADS = 32 * (E_NCONV + 2 + E_EPI1 + E_EPI2);
+constexpr int E_VRING = 12;                          // view planes
+constexpr int E_VS = 17 * 128;                       // [130 px][16 B]
+constexpr int E_ARING = 8;                           // a1 slabs (S1_SLAB bytes each)
+constexpr int E_NACC1 = 4, E_NACC2 = 12;             // TMEM: 4 x 32 columns for c1, 12 x 32 for the c2 ring
+constexpr int E_DONE = 16;
+constexpr int E_OFF_W1 = W_BYTES;
+constexpr int E_OFF_A1 = W_BYTES + 6 * 1024;
+constexpr int E_OFF_V = E_OFF_A1 + E_ARING * S1_SLAB;
+constexpr int E_OFF_BARS = E_OFF_V + E_VRING * E_VS;
+constexpr int E_SMEM = E_OFF_BARS + 1024;
+static_assert(E_OFF_A1 % 1024 == 0, "a1 slabs need the 512-byte swizzle period");
+
+struct EBars {
+  uint64_t v_full[E_VRING], a1_full[E_ARING], acc1_empty[E_NACC1], acc2_empty[E_NACC2], c1_done[E_DONE], c2_done[E_DONE];
+  uint32_t tmem_base;
+};
+
+template <bool IS_VIEWS, typename TIN>
+__global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in, const float* __restrict__ w1_oihw,
+                                                      const float* __restrict__ bias1, const float* __restrict__ w2_oihw,
+                                                      const float* __restrict__ bias2, __nv_bfloat16* __restrict__ out,
+                                                      int B, int H, int Wm, int tune) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w2 = smem;
+  uint8_t* s_w1 = smem + E_OFF_W1;
+  uint8_t* s_a1 = smem + E_OFF_A1;
+  uint8_t* s_v = smem + E_OFF_V;
+  EBars* bars = reinterpret_cast<EBars*>(smem + E_OFF_BARS);
+  __shared__ float s_b1[C], s_b2[C];
+  __shared__ float s_lut[256];
+  c1_fill_lut(s_lut);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wtiles = (Wm + E_STRIP - 1) / E_STRIP;
+  const int hsegs = (H + E_ROWS - 1) / E_ROWS;
+  const int items = B * wtiles * hsegs;
+
+  // c2 weights: [kw][cg][slot = 2 - kh][co][8 ci] (the s1 kernel's B operand); c1 weights: [kh][pair][kchunk][co][8 ch]
+  for (int i = tid; i < 9 * C * C; i += E_THREADS) {
+    const int ci = i & 31, co = (i >> 5) & 31, tap = i >> 10;
+    const int kh = tap / 3, kw = tap - 3 * kh;
+    *reinterpret_cast<__nv_bfloat16*>(s_w2 + (kw * 4 + (ci >> 3)) * S1_WN + ((2 - kh) * 32 + co) * 16 + (ci & 7) * 2) =
+        __float2bfloat16_rn(w2_oihw[(co * C + ci) * 9 + tap]);
+  }
+  for (int i = tid; i < 6 * 1024 / 2; i += E_THREADS) {
+    const int ch = i & 7, co = (i >> 3) & 31, kc = (i >> 8) & 1, pr = (i >> 9) & 1, kh = i >> 10;
+    const int kw = 2 * pr + kc;
+    const float v = (kw < 3 && ch < 3) ? w1_oihw[((co * 3 + ch) * 3 + kh) * 3 + kw] : 0.f;
+    reinterpret_cast<__nv_bfloat16*>(s_w1)[i] = __float2bfloat16_rn(v);
+  }
+  for (int i = tid; i < (E_ARING * S1_SLAB + E_VRING * E_VS) / 16; i += E_THREADS)      // slab pixels 128, 129 stay zero
+    reinterpret_cast<uint4*>(s_a1)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < C) { s_b1[tid] = bias1[tid]; s_b2[tid] = bias2[tid]; }
+  if (tid == 0) {
+    for (int i = 0; i < E_VRING; ++i) umma::mbar_init(&bars->v_full[i], 1);
+    for (int i = 0; i < E_ARING; ++i) umma::mbar_init(&bars->a1_full[i], 4);
+    for (int i = 0; i < E_NACC1; ++i) umma::mbar_init(&bars->acc1_empty[i], 4);
+    for (int i = 0; i < E_NACC2; ++i) umma::mbar_init(&bars->acc2_empty[i], 4);
+    for (int i = 0; i < E_DONE; ++i) { umma::mbar_init(&bars->c1_done[i], 1); umma::mbar_init(&bars->c2_done[i], 1); }
+    umma::fence_mbar_init();
+  }
+  if (warp == E_MMA_WARP) umma::tmem_alloc(&bars->tmem_base, 512);
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
+  const uint32_t tmem2 = tmem + E_NACC1 * 32;
+
+  if (warp < E_NCONV) {
+    // =========================== converters: plane gv -> warp gv % E_NCONV ==========================
+    uint32_t gvb = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int h0 = hs * E_ROWS;
+      const int rows = min(E_ROWS, H - h0);
+      for (int v = 0; v < rows + 4; ++v) {
+        const uint32_t gv = gvb + v;
+        if ((gv % E_NCONV) != (uint32_t)warp) continue;
+        if (gv >= E_VRING) {                                 // the c1 batch that last read this slot's previous plane
+          const uint32_t d = gv - E_VRING;
+          umma::mbar_wait(&bars->c1_done[d % E_DONE], (d / E_DONE) & 1);
+        }
+        if (!((tune >> 7) & 1)) c1_load_row<IS_VIEWS, TIN>(s_v + (gv % E_VRING) * E_VS, in, b, h0 - 2 + v, wt * E_STRIP - 2, H, Wm, lane, s_lut);
+        umma::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bars->v_full[gv % E_VRING]);
+      }
+      gvb += rows + 4;
+    }
+  } else if (warp == E_MMA_WARP) {
+    // =========================== c1 issuer: a1 row u of the item from planes u, u+1, u+2 ============
+    constexpr uint32_t idesc32 = umma::make_idesc_bf16(TILE_M, 32, false, false);
+    constexpr uint32_t ab_hi = umma::desc_hi(128);                            // A and B: SWIZZLE_NONE, SBO = 128
+    const uint32_t v_lo0 = umma::desc_lo(umma::smem_u32(s_v), 16);            // second K chunk = next pixel
+    const uint32_t w1_lo0 = umma::desc_lo(umma::smem_u32(s_w1), 512);
+    uint32_t gvb = 0, gab = 0, v_waited = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int hs = (it / wtiles) % hsegs;
+      const int rows = min(E_ROWS, H - hs * E_ROWS);
+      const int na = rows + 2;
+      for (int u = 0; u < na; ++u) {
+        for (; v_waited < gvb + u + 3; ++v_waited) umma::mbar_wait(&bars->v_full[v_waited % E_VRING], (v_waited / E_VRING) & 1);
+        const uint32_t a = gab + u, buf = a % E_NACC1;
+        umma::mbar_wait(&bars->acc1_empty[buf], ((a / E_NACC1) & 1) ^ 1);
+        umma::tc_fence_after_sync();
+        if (umma::elect_one()) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t pl = v_lo0 + ((gvb + u + kh) % E_VRING) * (E_VS >> 4);
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr)
+              umma::mma_bf16_lohi(tmem + buf * 32, pl + 2 * pr, ab_hi, w1_lo0 + ((kh * 2 + pr) * 1024 >> 4), ab_hi, idesc32,
+                                  (kh | pr) ? 1u : 0u);
+          }
+          umma::mma_commit(&bars->c1_done[(gvb + u) % E_DONE]);
+          if (u == na - 1) {                               // planes na, na+1 of the item have no batch of their own
+            umma::mma_commit(&bars->c1_done[(gvb + na) % E_DONE]);
+            umma::mma_commit(&bars->c1_done[(gvb + na + 1) % E_DONE]);
+          }
+        }
+        __syncwarp();
+      }
+      gvb += rows + 4; gab += na;
+    }
+  } else if (warp == E_MMA2_WARP) {
+    // =========================== c2 issuer: a1 row s feeds output rows s-2 (kh = 2), s-1 (kh = 1), s (kh = 0) =====
+    constexpr uint32_t idesc32 = umma::make_idesc_bf16(TILE_M, 32, false, false);
+    constexpr uint32_t IDESC_NSTEP = (32u >> 3) << 17;
+    constexpr uint32_t b_hi = umma::desc_hi(128);
+    constexpr uint32_t a2_hi = umma::desc_hi_sw64(512);                       // A: K-major SWIZZLE_64B
+    const uint32_t a1_lo0 = umma::desc_lo(umma::smem_u32(s_a1), 0);
+    const uint32_t w2_lo0 = umma::desc_lo(umma::smem_u32(s_w2), S1_WN);
+    uint32_t gab = 0, grb = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int hs = (it / wtiles) % hsegs;
+      const int rows = min(E_ROWS, H - hs * E_ROWS);
+      const int na = rows + 2;
+      for (int s = 0; s < na; ++s) {
+        const uint32_t a = gab + s;
+        umma::mbar_wait(&bars->a1_full[a % E_ARING], (a / E_ARING) & 1);
+        const bool is_new = s < rows;
+        if (is_new) {
+          const uint32_t rr = grb + s;
+          umma::mbar_wait(&bars->acc2_empty[rr % E_NACC2], ((rr / E_NACC2) & 1) ^ 1);
+        }
+        umma::tc_fence_after_sync();
+        if (umma::elect_one()) {
+          const uint32_t slab_lo = a1_lo0 + (a % E_ARING) * (S1_SLAB >> 4);
+          const int jlo = max(s - 2, 0), jhi = min(s, rows - 1);
+          const int n = jhi - jlo + 1;                      // output rows fed: 1..3
+          const int blk = jlo - (s - 2);                    // their first kh slot in B
+          const uint32_t sl = (grb + jlo) % E_NACC2;
+          const int n1 = min(n, (int)(E_NACC2 - sl));       // rows before the accumulator ring wraps
+          const uint32_t d0 = tmem2 + sl * 32;
+          const uint32_t i0 = idesc32 + (n1 - 1) * IDESC_NSTEP, i1 = idesc32 + (n - n1 - 1) * IDESC_NSTEP;
+          const uint32_t bo0 = blk * 32, bo1 = (blk + n1) * 32;
+          const bool two = n > n1;
+          const int no = is_new ? n - 1 : n;                // rows that already hold partial sums
+          const int no1 = min(no, n1), no2 = no - no1;
+#define E_AT(t) (slab_lo + (((((t) >> 1) * 64) + ((t) & 1) * 32) >> 4))
+#define E_BT(t) (w2_lo0 + ((((((t) >> 1) * 4) + 2 * ((t) & 1)) * S1_WN) >> 4))
+          if (no1 > 0) umma::mma_bf16_lohi(d0, slab_lo, a2_hi, w2_lo0 + bo0, b_hi, idesc32 + (no1 - 1) * IDESC_NSTEP, 1u);
+          if (no2 > 0) umma::mma_bf16_lohi(tmem2, slab_lo, a2_hi, w2_lo0 + bo1, b_hi, idesc32 + (no2 - 1) * IDESC_NSTEP, 1u);
+          if (is_new)
+            umma::mma_bf16_lohi(tmem2 + ((grb + jhi) % E_NACC2) * 32, slab_lo, a2_hi, w2_lo0 + (blk + n - 1) * 32, b_hi, idesc32, 0u);
+#pragma unroll
+          for (int t = 1; t < 6; ++t) {
+            umma::mma_bf16_lohi(d0, E_AT(t), a2_hi, E_BT(t) + bo0, b_hi, i0, 1u);
+            if (two) umma::mma_bf16_lohi(tmem2, E_AT(t), a2_hi, E_BT(t) + bo1, b_hi, i1, 1u);
+          }
+#undef E_AT
+#undef E_BT
+          umma::mma_commit(&bars->c2_done[a % E_DONE]);
+        }
+        __syncwarp();
+      }
+      gab += na; grb += rows;
+    }
+  } else if (warp < E_MMA2_WARP + 1 + E_EPI1) {
+    // =========================== epilogue 1: a1 row TMEM -> bias + ReLU -> bf16 -> swizzled slab ====
+    const int quarter = warp & 3;
+    const uint32_t half = (uint32_t)(warp - (E_MMA2_WARP + 1)) >> 2;     // this warp takes a1 rows with (counter & 1) == half
+    const int m = quarter * 32 + lane;                       // a1 pixel of the strip: mosaic column x0 - 1 + m
+    const uint32_t sw = (uint32_t)((m >> 1) & 3);
+    const uint32_t a1_base = umma::smem_u32(s_a1) + m * 64;
+    float bs[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) bs[k] = s_b1[k];
+    uint32_t gvb = 0, gab = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs;
+      const int h0 = hs * E_ROWS;
+      const int rows = min(E_ROWS, H - h0);
+      const int col = wt * E_STRIP - 1 + m;
+      const bool col_ok = col >= 0 && col < Wm;
+      for (int t = (int)((gab ^ half) & 1); t < rows + 2; t += 2) {
+        const uint32_t a = gab + t, buf = a % E_NACC1, dv = gvb + t;
+        umma::mbar_wait(&bars->c1_done[dv % E_DONE], (dv / E_DONE) & 1);
+        umma::tc_fence_after_sync();
+        uint32_t r[32];
+        umma::tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + buf * 32, r);
+        umma::tmem_ld_wait();
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive_relaxed(&bars->acc1_empty[buf]);
+        if (a >= E_ARING) {                                  // the c2 batch that read this slab's previous row
+          const uint32_t d = a - E_ARING;
+          umma::mbar_wait(&bars->c2_done[d % E_DONE], (d / E_DONE) & 1);
+        }
+        const int ha = h0 - 1 + t;
+        const uint32_t keep = (col_ok && ha >= 0 && ha < H) ? 0xffffffffu : 0u;     // outside the image a1 is c2's zero padding
+        const uint32_t dst = a1_base + (a % E_ARING) * S1_SLAB;
+        if (!((tune >> 6) & 1))
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(__uint_as_float(r[8 * c + 2 * k]) + bs[8 * c + 2 * k], 0.f),
+                                                     fmaxf(__uint_as_float(r[8 * c + 2 * k + 1]) + bs[8 * c + 2 * k + 1], 0.f));
+            pk[k] = *reinterpret_cast<uint32_t*>(&h) & keep;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((c ^ sw) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                       "r"(pk[3]) : "memory");
+        }
+        umma::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bars->a1_full[a % E_ARING]);
+      }
+      gvb += rows + 4; gab += rows + 2;
+    }
+  } else {
+    // =========================== epilogue 2: a2 row TMEM -> bias + ReLU -> bf16 -> HBM ==============
+    const int quarter = warp & 3;
+    const uint32_t half = (uint32_t)(warp - (E_MMA2_WARP + 1 + E_EPI1)) >> 2;
+    const int m = quarter * 32 + lane;
+    float bs[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) bs[k] = s_b2[k];
+    uint32_t gab = 0, grb = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int wt = it % wtiles, hs = (it / wtiles) % hsegs, b = it / (wtiles * hsegs);
+      const int h0 = hs * E_ROWS;
+      const int rows = min(E_ROWS, H - h0);
+      const int wo = wt * E_STRIP + m;
+      const bool ok = m < E_STRIP && wo < Wm;
+      for (int j = (int)((grb ^ half) & 1); j < rows; j += 2) {
+        const uint32_t rr = grb + j, slot = rr % E_NACC2, d = gab + j + 2;
+        if ((tune >> 5) & 1) umma::mbar_wait(&bars->c2_done[d % E_DONE], (d / E_DONE) & 1);
+        else mbar_wait_relaxed(&bars->c2_done[d % E_DONE], (d / E_DONE) & 1);
+        umma::tc_fence_after_sync();
+        uint32_t r[32];
+        umma::tmem_ld_32x32(tmem2 + ((uint32_t)(quarter * 32) << 16) + slot * 32, r);
+        umma::tmem_ld_wait();
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive_relaxed(&bars->acc2_empty[slot]);
+        if (ok && !((tune >> 8) & 1)) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(__uint_as_float(r[2 * k]) + bs[2 * k], 0.f),
+                                                     fmaxf(__uint_as_float(r[2 * k + 1]) + bs[2 * k + 1], 0.f));
+            pk[k] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          __nv_bfloat16* dst = out + (((size_t)b * H + h0 + j) * Wm + wo) * C;
+          umma::stg256(dst, pk);
+          umma::stg256(dst + 16, pk + 8);
+        }
+      }
+      gab += rows + 2; grb += rows;
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == E_MMA_WARP) umma::tmem_dealloc(tmem, 512);
+}
+
+
 }  // namespace
 
 
@@ -971,6 +1277,25 @@ int conv_c1_fwd_tc(const void* in, int in_flags, const float* w, const float* bi
   const bool views = in_flags & 1, u8 = in_flags & 2;
   if (u8) return views ? launch1(conv_c1_tc_kernel<true, uint8_t>, (const uint8_t*)in) : launch1(conv_c1_tc_kernel<false, uint8_t>, (const uint8_t*)in);
   return views ? launch1(conv_c1_tc_kernel<true, float>, (const float*)in) : launch1(conv_c1_tc_kernel<false, float>, (const float*)in);
+}
+
+// relu(c1) -> relu(c2) of the encoder in one kernel (inference: the first activation is not kept); out = a2, bf16 NHWC
+int enc_c1c2_fused_fwd_tc(const void* in, int in_flags, const float* w1, const float* b1, const float* w2, const float* b2,
+                          void* out, int B, int H, int Wm, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(out) & 31) != 0) return fail(DD_ERR_ALIGNMENT, "enc_c1c2_fused: out %p is not 32-byte aligned", out);
+  const int items = B * ((Wm + E_STRIP - 1) / E_STRIP) * ((H + E_ROWS - 1) / E_ROWS);
+  const int grid = items < kSMs ? items : kSMs;
+  auto launch1 = [&](auto k, auto* typed_in) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fail((int)e, "enc_c1c2_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    static const int tune = [] { const char* e = getenv("DD_ENC_TUNE"); return e ? atoi(e) : 0; }();
+    k<<<grid, E_THREADS, E_SMEM, st>>>(typed_in, w1, b1, w2, b2, (__nv_bfloat16*)out, B, H, Wm, tune);
+    return check_launch("enc_c1c2_fused");
+  };
+  const bool views = in_flags & 1, u8 = in_flags & 2;
+  if (u8) return views ? launch1(enc_c1c2_fused_kernel<true, uint8_t>, (const uint8_t*)in) : launch1(enc_c1c2_fused_kernel<false, uint8_t>, (const uint8_t*)in);
+  return views ? launch1(enc_c1c2_fused_kernel<true, float>, (const float*)in) : launch1(enc_c1c2_fused_kernel<false, float>, (const float*)in);
 }
 
 }  // namespace dd

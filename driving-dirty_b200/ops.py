@@ -126,7 +126,7 @@ class EncoderConvStack(torch.autograd.Function):
     """relu(c1) -> relu(c2) -> relu(c3, stride 2) -> view(B,-1) -> max_pool1d(4)
     (components.py:41-47).  ``inp`` is the views batch [B,6,3,H,W] (stitch folded into c1's loads)
     or a mosaic / NCHW image [B,3,H,Wm].  Activations are NHWC in ``act_dtype``.  Returns the
-    pooled features [B, 8*H3*W3] (act_dtype) or, with ``c3_only``, the c3 activation as NCHW fp32
+    pooled features [B, 8*H3*W3] (act_dtype; fp32 copies of the same values when nothing requires grad) or, with ``c3_only``, the c3 activation as NCHW fp32
     (components.py:44-45; ``c3_only == 2``: as the NHWC activation itself)."""
 
     @staticmethod
@@ -148,12 +148,21 @@ class EncoderConvStack(torch.autograd.Function):
         H3, W3 = (H - 1) // 2 + 1, (Wm - 1) // 2 + 1
         w1, b1, w2, b2, w3, b3 = (_c(t.detach().float()) for t in (w1, b1, w2, b2, w3, b3))
         in_flags = (_lib.IN_VIEWS if is_views else 0) | (_lib.IN_U8 if inp.dtype == torch.uint8 else 0)
-        a1 = torch.empty(B, H, Wm, 32, dtype=act_dtype, device=dev)
-        call("dd_conv_c1_fwd", inp.data_ptr(), in_flags, w1.data_ptr(), b1.data_ptr(), a1.data_ptr(), code,
-             B, H, Wm, impl, st)
-        a2 = torch.empty_like(a1)
-        call("dd_conv3x3_c32_fwd", a1.data_ptr(), w2.data_ptr(), b2.data_ptr(), a2.data_ptr(), code, B, H, Wm, 1,
-             impl, st)
+        inference = not any(ctx.needs_input_grad)
+        if inference and act_dtype == torch.bfloat16 and impl != _lib.IMPL_SIMT:
+            # no backward pass will ask for the first activation: c1 -> c2 in one kernel, a1 stays in shared memory / TMEM
+            # (same bits as the two kernels below)
+            a1 = None
+            a2 = torch.empty(B, H, Wm, 32, dtype=act_dtype, device=dev)
+            call("dd_encoder_c1c2_fused_fwd", inp.data_ptr(), in_flags, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                 b2.data_ptr(), a2.data_ptr(), B, H, Wm, st)
+        else:
+            a1 = torch.empty(B, H, Wm, 32, dtype=act_dtype, device=dev)
+            call("dd_conv_c1_fwd", inp.data_ptr(), in_flags, w1.data_ptr(), b1.data_ptr(), a1.data_ptr(), code,
+                 B, H, Wm, impl, st)
+            a2 = torch.empty_like(a1)
+            call("dd_conv3x3_c32_fwd", a1.data_ptr(), w2.data_ptr(), b2.data_ptr(), a2.data_ptr(), code, B, H, Wm, 1,
+                 impl, st)
         a3 = torch.empty(B, H3, W3, 32, dtype=act_dtype, device=dev)
         call("dd_conv3x3_c32_fwd", a2.data_ptr(), w3.data_ptr(), b3.data_ptr(), a3.data_ptr(), code, B, H, Wm, 2,
              impl, st)
@@ -162,7 +171,7 @@ class EncoderConvStack(torch.autograd.Function):
         elif c3_only:
             out = torch.empty(B, 32, H3, W3, dtype=torch.float32, device=dev)
             call("dd_nhwc_to_nchw_f32", a3.data_ptr(), code, out.data_ptr(), B, 32, H3, W3, st)
-        elif not any(ctx.needs_input_grad):
+        elif inference:
             # inference: fp32 features (exactly the bf16 maxima) -- the tf32 linear that follows reads them as they are
             out = torch.empty(B, 8 * H3 * W3, dtype=torch.float32, device=dev)
             call("dd_pool4_fwd_f32", a3.data_ptr(), out.data_ptr(), code, B, H3, W3, st)
@@ -170,7 +179,8 @@ class EncoderConvStack(torch.autograd.Function):
             out = torch.empty(B, 8 * H3 * W3, dtype=act_dtype, device=dev)
             call("dd_pool4_fwd", a3.data_ptr(), out.data_ptr(), code, B, H3, W3, st)
         ctx.geom = (B, H, Wm, H3, W3, in_flags, code, c3_only, impl, act_dtype)
-        ctx.save_for_backward(inp, w2, w3, a1, a2, a3)
+        if not inference:
+            ctx.save_for_backward(inp, w2, w3, a1, a2, a3)
         return out
 
     @staticmethod

@@ -70,6 +70,11 @@ int dd_u8_to_f32(const uint8_t* in, float* out, long long n, void* stream);
 enum { DD_IN_VIEWS = 1, DD_IN_U8 = 2 };
 int dd_conv_c1_fwd(const void* in, int in_flags, const float* w_oihw, const float* bias,
                    void* out, int out_dtype, int B, int H, int Wm, int impl, void* stream);
+/* Inference front of the encoder in one kernel: a2 = relu(c2(relu(c1(x)))) (components.py:41-43), bf16 NHWC [B,H,Wm,32];
+ * the first activation stays in shared memory / TMEM (halo recompute per 126-pixel x 64-row strip).  Same bits as
+ * dd_conv_c1_fwd + dd_conv3x3_c32_fwd on the bf16 tensor-core path.  in / in_flags as for dd_conv_c1_fwd. */
+int dd_encoder_c1c2_fused_fwd(const void* in, int in_flags, const float* w1_oihw, const float* bias1,
+                              const float* w2_oihw, const float* bias2, void* a2, int B, int H, int Wm, void* stream);
 /* dW [32,3,3,3], db [32] from dy = dL/d(out) ALREADY masked by out>0.  workspace: see below. */
 int dd_conv_c1_wgrad(const void* in, int in_flags, const void* dy, int dtype, float* dw,
                      float* db, void* workspace, size_t ws_bytes, int B, int H, int Wm, int impl,

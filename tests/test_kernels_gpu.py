@@ -284,6 +284,34 @@ def test_conv_c1_tcgen05_raw_bytes_and_full_size(dd, B, H, W):
              torch.empty(B, H, Wm, 32, device="cuda").data_ptr(), dtype_code(torch.float32), B, H, Wm, 0, st)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 16, 20), (1, 33, 7), (2, 70, 50), (1, 1, 22), (3, 130, 43), (2, 256, 306)])
+def test_encoder_c1c2_fused_bit_identical(dd, B, H, W):
+    """dd_encoder_c1c2_fused_fwd (inference: the first activation never leaves the SM) against the two-kernel tensor-core
+    path it replaces: BIT-IDENTICAL a2 (a1 is rounded to bf16 at the same point and the MMAs see the same operands in the
+    same order), for views, raw bytes and a mosaic, ragged strips (Wm % 126 != 0), short / single rows and several row
+    segments; and within bf16 tolerance of the fp32 reference convs (components.py:41-43)."""
+    from driving_dirty_b200._lib import call, dtype_code, stream_ptr
+    g = torch.Generator().manual_seed(35 + H)
+    raw = torch.randint(0, 256, (B, 6, 3, H, W), dtype=torch.uint8, generator=g)
+    views = raw.float() / 255
+    _, w1, b1 = _conv_inputs(1, 4, 4, seed=36, cin=3)
+    _, w2, b2 = _conv_inputs(1, 4, 4, seed=37)
+    Wm, st, code = 6 * W, stream_ptr(), dtype_code(torch.bfloat16)
+    w1c, b1c, w2c, b2c = w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda()
+    vd = views.cuda()
+    a1 = torch.empty(B, H, Wm, 32, dtype=torch.bfloat16, device="cuda")
+    a2 = torch.empty_like(a1)
+    call("dd_conv_c1_fwd", vd.data_ptr(), 1, w1c.data_ptr(), b1c.data_ptr(), a1.data_ptr(), code, B, H, Wm, 2, st)
+    call("dd_conv3x3_c32_fwd", a1.data_ptr(), w2c.data_ptr(), b2c.data_ptr(), a2.data_ptr(), code, B, H, Wm, 1, 2, st)
+    ref = F.relu(F.conv2d(F.relu(F.conv2d(so.stitch(views), w1, b1, padding=1)), w2, b2, padding=1))
+    assert rel_max_err(to_nchw(a2), ref) < BF16_TOL
+    for flags, src in ((1, vd), (3, raw.cuda()), (2, so.stitch(raw).cuda()), (0, so.stitch(views).cuda())):
+        fused = torch.full_like(a2, float("nan"))
+        call("dd_encoder_c1c2_fused_fwd", src.data_ptr(), flags, w1c.data_ptr(), b1c.data_ptr(), w2c.data_ptr(), b2c.data_ptr(),
+             fused.data_ptr(), B, H, Wm, st)
+        assert torch.equal(fused.view(torch.int16), a2.view(torch.int16)), f"flags {flags}"
+
+
 # ------------------------------------------------------------------------------- pool --------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W", [(2, 8, 60), (2, 5, 42), (1, 3, 7), (1, 128, 918)])
