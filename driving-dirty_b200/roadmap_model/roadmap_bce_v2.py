@@ -44,11 +44,13 @@ class RoadMapBCE(LightningModule):
         [0,1,2,5,4,3] (:53-64)."""
         return ops.stitch(sample)
 
-    def _logits(self, x):
-        z = self.ae.encoder.forward_views(x)          # stitch folded into the first conv
+    def _head(self, z):
         y = ops.linear(z, self.fc1.weight, self.fc1.bias, self.impl,
                        allow_tf32=self.ae.encoder.compute_dtype == torch.bfloat16)
         return y.reshape(y.size(0), self.map_size, self.map_size)
+
+    def _logits(self, x):
+        return self._head(self.ae.encoder.forward_views(x))          # stitch folded into the first conv
 
     def forward(self, x):
         """Returns ``(logits, sigmoid(logits))`` like the reference (:66-81)."""

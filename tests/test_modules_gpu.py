@@ -474,6 +474,24 @@ def test_run_test_driver_scores_match_per_scene_oracle(golden, tmp_path):
     assert abs(res["bounding_box_ats"] - want) < 1e-6 and res["scenes"] == g["batch"]
 
 
+def test_model_loader_pipelined_host_batch_equals_resident(golden):
+    """A page-locked host batch larger than ``pipeline_chunk`` is copied chunk by chunk under the conv stack; the dense tail
+    (and its dropout draw) still runs once over the whole batch: same bits as the device-resident call with the same seed,
+    for raw bytes and fp32 views, ragged last chunk included."""
+    from driving_dirty_b200.model_loader import ModelLoader
+    g, model, params, views, road = _load_case(golden, "roadmap_small", "bf16")
+    loader = ModelLoader(model, graph_max_batch=0, pipeline_chunk=3)
+    big = torch.cat([views, views.flip(0), views * 0.5, views[:1]], dim=0)          # 3 * B + 1 scenes
+    raw = (big * 255).round().to(torch.uint8)
+    for host in (raw, big):
+        pinned = host.pin_memory()
+        torch.manual_seed(91)
+        want = loader.get_binary_road_map(host.cuda(), as_bytes=True)
+        torch.manual_seed(91)
+        got = loader.get_binary_road_map(pinned, as_bytes=True)
+        assert got.shape[0] == host.shape[0] and torch.equal(got, want)
+
+
 def test_model_loader_cuda_graph_path_equals_eager(golden):
     """Batches up to ``graph_max_batch`` replay a captured CUDA graph: same bits as the eager forward for the same seed
     (the torch dropout inside the graph draws from the generator's Philox offset like the eager call), fresh masks per call."""
