@@ -104,7 +104,7 @@ class Encoder(nn.Module):
         return feats if self.c3_only else self._tail(feats)
 
     def forward_views(self, views):
-        feats = self._stack(ops.as_view_batch(views))
+        feats = self._stack(ops.as_view_batch(views, keep_bytes=True))
         return feats if self.c3_only else self._tail(feats)
 
 

@@ -56,7 +56,7 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
 // sub-partition, 11264 -- together exactly 16 K.  With 96 registers here that kernel queued behind the whole update
 // (1.8 ms hole in the N = 2 multicast timeline, profiles/r2_step_timeline_n2_multicast_96regs.txt).
 template <int MODE, int UNROLL>
-__global__ void __maxnreg__(80) adam_kernel(PeerPtrs pp, const float* __restrict__ mc_grad, float* __restrict__ mc_param,
+__global__ void __maxnreg__(MODE == 0 ? 96 : 80) adam_kernel(PeerPtrs pp, const float* __restrict__ mc_grad, float* __restrict__ mc_param,
                                                         float* __restrict__ m, float* __restrict__ v, long long off,
                                                         long long n, int world, int rank, AdamHyper h) {
   // element i of the shard is element off + i of the full tensors; n and off are multiples of 4

@@ -309,7 +309,7 @@ int launch_dil(const void* in, const __nv_bfloat16* wp, const float* bias, const
   g.items = g.B * g.D * g.groups_max * g.strips;
   auto k = conv_dil_tc_kernel<KC, N, G>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
-  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  dd::prefer_max_smem(k);
   if (e != cudaSuccess) return dd::fail((int)e, "conv_dil_tc: cudaFuncSetAttribute(%d): %s", T::SMEM, cudaGetErrorString(e));
   CUtensorMap min_, mw;
   {

@@ -291,12 +291,12 @@ int conv_dil_wgrad_tc(const void* in, const void* dout, float* dw, long long sn,
   cudaError_t e;
   if (N == 64) {
     e = cudaFuncSetAttribute(conv_dil_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(conv_dil_wgrad_tc_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    dd::prefer_max_smem(conv_dil_wgrad_tc_kernel<64>);
     if (e != cudaSuccess) return fail((int)e, "conv_dil_wgrad_tc: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
     conv_dil_wgrad_tc_kernel<64><<<grid, WGD_THREADS, smem, st>>>(mx, md, (float*)ws, g);
   } else {
     e = cudaFuncSetAttribute(conv_dil_wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(conv_dil_wgrad_tc_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    dd::prefer_max_smem(conv_dil_wgrad_tc_kernel<32>);
     if (e != cudaSuccess) return fail((int)e, "conv_dil_wgrad_tc: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
     conv_dil_wgrad_tc_kernel<32><<<grid, WGD_THREADS, smem, st>>>(mx, md, (float*)ws, g);
   }

@@ -22,7 +22,6 @@
 // full/empty (4 x 32 TMEM columns), so loads, MMAs and epilogues of different rows overlap.
 #include "dd_common.cuh"
 
-#include <cstdlib>
 #include "tma_host.h"
 #include "umma.cuh"
 
@@ -227,7 +226,7 @@ int launch_s2_fwd(const void* in, const float* w, const float* bias, void* out, 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int items = B * ((Wo + TILE_M - 1) / TILE_M) * ((Ho + ROWS - 1) / ROWS);
   cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_s2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM);
-  cudaFuncSetAttribute(conv3x3_c32_s2_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  dd::prefer_max_smem(conv3x3_c32_s2_tc_kernel);
   if (e != cudaSuccess) return dd::fail((int)e, "conv_tc s2: cudaFuncSetAttribute(%d): %s", S2_SMEM, cudaGetErrorString(e));
   CUtensorMap m2, m1;
   int r = dd::tma_map_nhwc_sw64(&m2, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, 255, 2);      // 255 source pixels -> 128 loaded
@@ -521,7 +520,7 @@ int launch_s1(const void* in, const float* w, const float* bias, const void* mas
   const int items = B * ((W + TILE_M - 1) / TILE_M) * ((H + S1_ROWS - 1) / S1_ROWS);
   auto k = conv3x3_c32_s1_tc_kernel<MODE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S1_SMEM);
-  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  dd::prefer_max_smem(k);
   if (e != cudaSuccess) return dd::fail((int)e, "conv_tc s1: cudaFuncSetAttribute(%d): %s", S1_SMEM, cudaGetErrorString(e));
   const int grid = items < dd::kSMs ? items : dd::kSMs;
   if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return dd::fail(DD_ERR_ALIGNMENT, "conv_tc s1: input is not 16-byte aligned");
@@ -923,8 +922,10 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __
 // The first activation (963 MB per 32 scenes as bf16) never touches HBM: a CTA walks a strip of 126 output
 // pixels down 64 rows; per row
 //   converter warps   views / mosaic row (fp32 or raw bytes) -> [130 px][8 ch] bf16 plane      (as conv_c1_tc_kernel)
-//   MMA warp          c1: 6 MMAs (M=128, N=32) over three planes -> TMEM;  c2: row-scatter MMAs (as the s1 kernel) over
-//                     the a1 slab the first epilogue wrote, E_LAG rows behind
+//   two MMA warps     c1: 6 MMAs (M=128, N=32) over three planes -> TMEM;  c2: row-scatter MMAs (as the s1 kernel) over
+//                     the a1 slab the first epilogue wrote.  Two issuing threads because every mbarrier wait and
+//                     tcgen05.commit costs its thread 100-200 cycles: one thread doing both batches left the pipe idle
+//                     60 % of the time (0.76 ms per 32 scenes; two issuers + 8-warp epilogues: 0.50)
 //   epilogue 1        TMEM -> bias + ReLU -> bf16 -> shared memory, in the K-major SWIZZLE_64B layout the c2 MMAs read
 //                     ([130 px][32 ch], 64-byte rows, 16-byte chunk ^= (px >> 1) & 3); pixels / rows outside the image
 //                     are written as ZERO (c2's padding), not as relu(bias)
@@ -964,7 +965,7 @@ template <bool IS_VIEWS, typename TIN>
 __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in, const float* __restrict__ w1_oihw,
                                                       const float* __restrict__ bias1, const float* __restrict__ w2_oihw,
                                                       const float* __restrict__ bias2, __nv_bfloat16* __restrict__ out,
-                                                      int B, int H, int Wm, int tune) {
+                                                      int B, int H, int Wm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w2 = smem;
   uint8_t* s_w1 = smem + E_OFF_W1;
@@ -1026,7 +1027,7 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
           const uint32_t d = gv - E_VRING;
           umma::mbar_wait(&bars->c1_done[d % E_DONE], (d / E_DONE) & 1);
         }
-        if (!((tune >> 7) & 1)) c1_load_row<IS_VIEWS, TIN>(s_v + (gv % E_VRING) * E_VS, in, b, h0 - 2 + v, wt * E_STRIP - 2, H, Wm, lane, s_lut);
+        c1_load_row<IS_VIEWS, TIN>(s_v + (gv % E_VRING) * E_VS, in, b, h0 - 2 + v, wt * E_STRIP - 2, H, Wm, lane, s_lut);
         umma::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(&bars->v_full[gv % E_VRING]);
@@ -1156,7 +1157,6 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
         const int ha = h0 - 1 + t;
         const uint32_t keep = (col_ok && ha >= 0 && ha < H) ? 0xffffffffu : 0u;     // outside the image a1 is c2's zero padding
         const uint32_t dst = a1_base + (a % E_ARING) * S1_SLAB;
-        if (!((tune >> 6) & 1))
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[4];
@@ -1192,8 +1192,7 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
       const bool ok = m < E_STRIP && wo < Wm;
       for (int j = (int)((grb ^ half) & 1); j < rows; j += 2) {
         const uint32_t rr = grb + j, slot = rr % E_NACC2, d = gab + j + 2;
-        if ((tune >> 5) & 1) umma::mbar_wait(&bars->c2_done[d % E_DONE], (d / E_DONE) & 1);
-        else mbar_wait_relaxed(&bars->c2_done[d % E_DONE], (d / E_DONE) & 1);
+        mbar_wait_relaxed(&bars->c2_done[d % E_DONE], (d / E_DONE) & 1);
         umma::tc_fence_after_sync();
         uint32_t r[32];
         umma::tmem_ld_32x32(tmem2 + ((uint32_t)(quarter * 32) << 16) + slot * 32, r);
@@ -1201,7 +1200,7 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
         umma::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive_relaxed(&bars->acc2_empty[slot]);
-        if (ok && !((tune >> 8) & 1)) {
+        if (ok) {
           uint32_t pk[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -1248,7 +1247,7 @@ int conv3x3_c32_fwd_tc(const void* in, const float* w, const float* bias, void* 
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const int items = B * (((W + 1) / 2 + TILE_M - 1) / TILE_M) * (((H + 1) / 2 + DG_MROWS - 1) / DG_MROWS);
     cudaError_t e = cudaFuncSetAttribute(conv3x3_c32_dgrad_s2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
-    cudaFuncSetAttribute(conv3x3_c32_dgrad_s2_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    dd::prefer_max_smem(conv3x3_c32_dgrad_s2_tc_kernel);
     if (e != cudaSuccess) return fail((int)e, "dgrad_s2_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) return fail(DD_ERR_ALIGNMENT, "dgrad_s2_tc: dy is not 16-byte aligned");
     CUtensorMap mdy;
@@ -1269,7 +1268,7 @@ int conv_c1_fwd_tc(const void* in, int in_flags, const float* w, const float* bi
   const int grid = items < kSMs ? items : kSMs;
   auto launch1 = [&](auto k, auto* typed_in) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM);
-    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    dd::prefer_max_smem(k);
     if (e != cudaSuccess) return fail((int)e, "conv_c1_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     k<<<grid, C1_THREADS, C1_SMEM, st>>>(typed_in, w, bias, (__nv_bfloat16*)out, B, H, Wm);
     return check_launch("conv_c1_tc");
@@ -1287,10 +1286,9 @@ int enc_c1c2_fused_fwd_tc(const void* in, int in_flags, const float* w1, const f
   const int grid = items < kSMs ? items : kSMs;
   auto launch1 = [&](auto k, auto* typed_in) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
-    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    dd::prefer_max_smem(k);
     if (e != cudaSuccess) return fail((int)e, "enc_c1c2_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    static const int tune = [] { const char* e = getenv("DD_ENC_TUNE"); return e ? atoi(e) : 0; }();
-    k<<<grid, E_THREADS, E_SMEM, st>>>(typed_in, w1, b1, w2, b2, (__nv_bfloat16*)out, B, H, Wm, tune);
+    k<<<grid, E_THREADS, E_SMEM, st>>>(typed_in, w1, b1, w2, b2, (__nv_bfloat16*)out, B, H, Wm);
     return check_launch("enc_c1c2_fused");
   };
   const bool views = in_flags & 1, u8 = in_flags & 2;

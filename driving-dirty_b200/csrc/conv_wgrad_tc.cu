@@ -552,7 +552,7 @@ int wgrad_ring_launch(const void* x, const void* dy, float* dw, float* db, void*
   float* dbp = partial + (size_t)grid * G::PARTIAL;
   auto k = conv3x3_c32_wgrad_ring_kernel<STRIDE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  dd::prefer_max_smem(k);
   if (e != cudaSuccess) return dd::fail((int)e, "wgrad_tc: cudaFuncSetAttribute(%d): %s", G::SMEM, cudaGetErrorString(e));
   CUtensorMap mx = {}, mx1 = {}, mdy = {};
   int r;
@@ -596,7 +596,7 @@ int conv_c1_wgrad_tc(const void* in, int in_flags, const void* dy, float* dw, fl
     return fail(DD_ERR_UNSUPPORTED, "tcgen05 c1 wgrad: cuTensorMapEncodeTiled(dy) -> %d", r);
   auto launch1 = [&](auto k, auto* typed_in) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM);
-    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    dd::prefer_max_smem(k);
     if (e != cudaSuccess) return fail((int)e, "conv_c1_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     k<<<grid, C1_THREADS, C1_SMEM, st>>>(typed_in, mdy, (float*)ws, B, H, Wm);
     return check_launch("conv_c1_wgrad_ring");

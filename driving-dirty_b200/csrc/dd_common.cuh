@@ -18,6 +18,18 @@ int check_launch(const char* what);  // cudaGetLastError -> return code, counts 
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Persistent kernels that live on big dynamic shared memory ask for the maximum shared-memory carveout: an SM changes its
+// L1 / shared split only when idle, so a kernel that needs more shared memory than the split chosen for the previous one
+// cannot join an SM that the overlapped optimizer update keeps busy (it queued behind the whole update at N > 1).
+template <class K>
+inline void prefer_max_smem(K kernel) {
+#ifndef DD_NO_CARVEOUT_PREFERENCE
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#else
+  (void)kernel;
+#endif
+}
+
 #define DD_REQUIRE(cond, code, ...) \
   do {                              \
     if (!(cond)) return dd::fail((code), __VA_ARGS__); \

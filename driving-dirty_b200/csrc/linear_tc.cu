@@ -399,7 +399,7 @@ int ceil_div_ll(long long a, long long b) { return (int)((a + b - 1) / b); }
 template <typename K>
 int set_smem(K kernel, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  dd::prefer_max_smem(kernel);
   if (e != cudaSuccess) return dd::fail((int)e, "linear_tc: cudaFuncSetAttribute(%d): %s", bytes, cudaGetErrorString(e));
   return 0;
 }

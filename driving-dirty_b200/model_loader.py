@@ -123,7 +123,7 @@ class ModelLoader:
         for k, (x, ev) in enumerate(staged):
             cur.wait_event(ev)
             x.record_stream(cur)                     # allocated on the copy stream, consumed here
-            f = enc._stack(ops.as_view_batch(x))
+            f = enc._stack(ops.as_view_batch(x, keep_bytes=True))
             if feats is None:
                 feats = torch.empty(B, f.shape[1], dtype=f.dtype, device=self.device)
             feats[k * c:k * c + f.shape[0]] = f

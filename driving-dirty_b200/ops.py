@@ -49,11 +49,12 @@ _ws = _Workspaces()
 # --------------------------------------------------------------------------------------------
 # input handling / stitch
 # --------------------------------------------------------------------------------------------
-def as_view_batch(sample) -> torch.Tensor:
+def as_view_batch(sample, keep_bytes=False) -> torch.Tensor:
     """tuple/list of B [6,3,H,W] tensors (what collate_fn yields) or a [B,6,3,H,W] tensor ->
     contiguous [B,6,3,H,W] fp32 CUDA tensor, without a copy when the tuple is ``batch.unbind(0)``.  uint8 raw camera
     bytes are taken as they come off the JPEG decoder: ToTensor's /255 (data_helper.py:109-114) runs here on the device
-    (``dd_u8_to_f32``, bit-identical to ``x.float() / 255``), so only a quarter of the bytes cross PCIe."""
+    (``dd_u8_to_f32``, bit-identical to ``x.float() / 255``), so only a quarter of the bytes cross PCIe.  ``keep_bytes``:
+    hand the uint8 batch on as it is (``encoder_conv_stack`` converts, or reads the bytes inside its fused inference kernel)."""
     if torch.is_tensor(sample):
         x = sample
     else:
@@ -68,7 +69,7 @@ def as_view_batch(sample) -> torch.Tensor:
     if x.dim() != 5 or x.shape[1] != 6 or x.shape[2] != 3:
         raise RuntimeError(f"expected views of shape [B,6,3,H,W], got {tuple(x.shape)}")
     if x.dtype == torch.uint8:
-        return bytes_to_float(x)
+        return _c(x) if keep_bytes else bytes_to_float(x)
     if x.dtype != torch.float32:
         x = x.float()
     return _c(x)
@@ -133,10 +134,13 @@ class EncoderConvStack(torch.autograd.Function):
     def forward(ctx, inp, w1, b1, w2, b2, w3, b3, act_dtype, c3_only, impl):
         _require_cuda(inp, w1, w2, w3)
         inp = _c(inp)
-        if inp.dtype == torch.uint8:
+        inference = not any(ctx.needs_input_grad)
+        fused_front = inference and act_dtype == torch.bfloat16 and impl != _lib.IMPL_SIMT
+        if inp.dtype == torch.uint8 and not fused_front:
             # raw camera bytes: ToTensor's /255 as a pass of its own (0.04 ms for 32 scenes).  The c1 kernels can also read
             # bytes directly (DD_IN_U8, bit-identical, tested), but their byte-granular loads keep too few bytes in flight:
-            # +0.26 ms per step measured (profiles/r2_kernel_times.txt), so the model path converts first.
+            # +0.26 ms per step measured (profiles/r2_kernel_times.txt), so the training path converts first.  The fused
+            # inference front is not bound by its converter warps: it reads the bytes itself (+0.03 ms against 0.08 for the pass)
             inp = bytes_to_float(inp)
         is_views = inp.dim() == 5
         if is_views:
@@ -148,8 +152,7 @@ class EncoderConvStack(torch.autograd.Function):
         H3, W3 = (H - 1) // 2 + 1, (Wm - 1) // 2 + 1
         w1, b1, w2, b2, w3, b3 = (_c(t.detach().float()) for t in (w1, b1, w2, b2, w3, b3))
         in_flags = (_lib.IN_VIEWS if is_views else 0) | (_lib.IN_U8 if inp.dtype == torch.uint8 else 0)
-        inference = not any(ctx.needs_input_grad)
-        if inference and act_dtype == torch.bfloat16 and impl != _lib.IMPL_SIMT:
+        if fused_front:
             # no backward pass will ask for the first activation: c1 -> c2 in one kernel, a1 stays in shared memory / TMEM
             # (same bits as the two kernels below)
             a1 = None

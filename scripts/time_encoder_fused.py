@@ -40,6 +40,13 @@ def timeit(fn, reps=10):
     ts.sort()
     return ts[len(ts) // 2]
 
+raw = (views * 255).round().to(torch.uint8)
+viewsq = raw.float() / 255
+def fused_u8():
+    call("dd_encoder_c1c2_fused_fwd", raw.data_ptr(), 3, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+         a2f.data_ptr(), B, H, Wm, st)
+t8 = timeit(fused_u8)
+print(f"fused from raw bytes {t8:.4f} ms")
 t2, tf = timeit(two), timeit(fused)
 same = torch.equal(a2.view(torch.int16), a2f.view(torch.int16))
 flops = 2.0 * B * H * Wm * 32 * (27 + 288)

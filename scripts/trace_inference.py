@@ -33,3 +33,16 @@ busy = sum(t for _, t in tot.values())
 print(f"batch {b} {dtype}: {len(evs)} device events, span {span:.3f} ms, sum of kernel times {busy:.3f} ms")
 for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"{t:8.3f} ms  {100 * t / span:5.1f} %  x{n:<4d} {k}")
+
+if os.environ.get("GAPS"):
+    print("gaps > 20 us between consecutive device events:")
+    for a, b in zip(evs, evs[1:]):
+        gap = (b.time_range.start - a.time_range.end) / 1e3
+        if gap > 0.02:
+            print(f"{gap:8.3f} ms after {a.name[:60]}  ->  {b.name[:60]}")
+    cpu = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU and e.time_range.elapsed_us() > 100]
+    cpu.sort(key=lambda e: e.time_range.start)
+    t0 = evs[0].time_range.start
+    print("host-side ops longer than 100 us (start relative to the first kernel, duration):")
+    for e in cpu:
+        print(f"{(e.time_range.start - t0) / 1e3:9.3f} ms  {e.time_range.elapsed_us() / 1e3:8.3f} ms  {e.name[:80]}")
