@@ -282,9 +282,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) conv_dil_tc_kernel(const __grid
 }
 
 // packed weights [chunk][kw][kappa][n][32 k] bf16 from a torch-layout fp32 tensor: element (n, k, kh, kw) sits at
-// w[n * sn + k * sk + kh * KT + kw]; kh = flip ? KT-1-kappa : kappa.  Channels k >= Kreal are zero.
+// w[n * sn + k * sk + kh * KT + kw]; kh = flip ? KT-1-kappa : kappa.  Channels k >= Kreal / n >= Nreal are zero.
 __global__ void dil_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int KC, int KT, int N, int Kreal,
-                                long long sn, long long sk, int flip) {
+                                int Nreal, long long sn, long long sk, int flip) {
   const long long total = (long long)KC * KT * KT * N * 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k32 = (int)(i & 31);
@@ -295,7 +295,7 @@ __global__ void dil_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __re
     const int c = (int)(rest / KT);
     const int k = c * 32 + k32;
     const int kh = flip ? KT - 1 - ka : ka;
-    wp[i] = __float2bfloat16_rn(k < Kreal ? w[n * sn + k * sk + (long long)kh * KT + kw] : 0.f);
+    wp[i] = __float2bfloat16_rn(k < Kreal && n < Nreal ? w[n * sn + k * sk + (long long)kh * KT + kw] : 0.f);
   }
 }
 
@@ -354,14 +354,18 @@ size_t conv_dil_tc_pack_bytes(int K, int N, int KT) { return (size_t)((K + 31) /
 // w: torch-layout fp32 weights; (sn, sk): strides of the produced / gathered channel index in it; flip: kh = KT-1-kappa
 int conv_dil_tc(const void* in, const float* w, long long sn, long long sk, int flip, const float* bias, const void* mask, void* out,
                 void* pack_ws, int B, int Hi, int Wi, int Ho, int Wo, int K, int N, int KT, int D, int sign, int off, int relu,
-                cudaStream_t st) {
+                cudaStream_t st, int Kreal, int Nreal) {
+  // Kreal < K: `in` carries K channels per pixel of which only the first Kreal exist in the weights (zero-padded pixels);
+  // Nreal < N: the weights have Nreal produced channels, `out` / bias / mask carry N (the caller drops the padding)
+  if (Kreal <= 0 || Kreal > K) Kreal = K;
+  if (Nreal <= 0 || Nreal > N) Nreal = N;
   if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask) |
         reinterpret_cast<uintptr_t>(pack_ws)) & 31) != 0)
     return fail(DD_ERR_ALIGNMENT, "conv_dil_tc: pointers must be 32-byte aligned");
   const int KC = K / 32;
   __nv_bfloat16* wp = (__nv_bfloat16*)pack_ws;
   const long long total = (long long)KC * KT * KT * N * 32;
-  dil_pack_kernel<<<(int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592), 256, 0, st>>>(w, wp, KC, KT, N, K, sn, sk, flip);
+  dil_pack_kernel<<<(int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592), 256, 0, st>>>(w, wp, KC, KT, N, Kreal, Nreal, sn, sk, flip);
   if (int e = check_launch("conv_dil_pack")) return e;
   DilGeo g = {};
   g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ho = Ho; g.Wo = Wo; g.KT = KT; g.D = D; g.sign = sign; g.off = off;

@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(WGD_THREADS, 1) conv_dil_wgrad_tc_kernel(const
 }
 
 // dw(n, k, kh, kw) at dw[n*sn + k*sk + kh*KT + kw] = sum over the CTAs of the type that owns (chunk of k, kw), fixed order
-__global__ void wgd_fold_kernel(const float* __restrict__ partial, float* __restrict__ dw, WgdGeo g, int N, int Kreal, long long sn,
-                                long long sk) {
+__global__ void wgd_fold_kernel(const float* __restrict__ partial, float* __restrict__ dw, WgdGeo g, int N, int Kreal, int Nreal,
+                                long long sn, long long sk) {
   const int ntypes = g.nchunks * g.nkwsets;
   const long long total = (long long)g.nchunks * 32 * g.KT * g.KT * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -208,7 +208,7 @@ __global__ void wgd_fold_kernel(const float* __restrict__ partial, float* __rest
     const int kw = (int)(rest % g.KT);
     const int chunk = (int)(rest / g.KT);
     const int k = chunk * 32 + k32;
-    if (k >= Kreal) continue;
+    if (k >= Kreal || n >= Nreal) continue;
     const int kwset = kw / g.kws, j = kw - kwset * g.kws;
     const int type = kwset * g.nchunks + chunk;
     float s = 0.f;
@@ -277,7 +277,11 @@ size_t conv_dil_wgrad_tc_ws_bytes(int K, int N, int KT) {
 // `in` [B,Hi,Wi,K] and `dout` [B,Ho,Wo,N] bf16 NHWC; dw: torch-layout fp32 weights with the produced / gathered channel
 // strides (sn, sk) -- the same convention as dd::conv_dil_tc.
 int conv_dil_wgrad_tc(const void* in, const void* dout, float* dw, long long sn, long long sk, void* ws, size_t ws_bytes, int B,
-                      int Hi, int Wi, int Ho, int Wo, int K, int N, int KT, int D, int sign, int off, cudaStream_t st) {
+                      int Hi, int Wi, int Ho, int Wo, int K, int N, int KT, int D, int sign, int off, cudaStream_t st, int Kreal,
+                      int Nreal) {
+  // Kreal < K / Nreal < N: zero-padded pixels; only dw[n < Nreal][k < Kreal] exists
+  if (Kreal <= 0 || Kreal > K) Kreal = K;
+  if (Nreal <= 0 || Nreal > N) Nreal = N;
   if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(dout)) & 15) != 0)
     return fail(DD_ERR_ALIGNMENT, "conv_dil_wgrad_tc: operands must be 16-byte aligned");
   WgdGeo g = make_geo(B, Ho, Wo, K, N, KT, D, sign, off);
@@ -302,7 +306,7 @@ int conv_dil_wgrad_tc(const void* in, const void* dout, float* dw, long long sn,
   }
   if (int err = check_launch("conv_dil_wgrad_tc")) return err;
   const long long total = (long long)g.nchunks * 32 * KT * KT * N;
-  wgd_fold_kernel<<<(int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, st>>>((const float*)ws, dw, g, N, K, sn, sk);
+  wgd_fold_kernel<<<(int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, st>>>((const float*)ws, dw, g, N, Kreal, Nreal, sn, sk);
   return check_launch("conv_dil_wgrad_fold");
 }
 

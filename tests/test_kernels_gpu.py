@@ -576,6 +576,7 @@ TC_LAYERS = {
     "up_conv1_96_64_k7d7": (True, 96, 64, 7, 0, 7, (20, 150), 2),
     "up_conv2_64_32_k7d7": (True, 64, 32, 7, 0, 7, (30, 140), 2),
     "up_conv3_32_16_k7d7": (True, 32, 16, 7, 0, 7, (33, 100), 1),
+    "up_conv4_16_8_k7d3": (True, 16, 8, 7, 0, 3, (37, 140), 2),     # all three passes through zero-padded 32-channel pixels
     "dc1_64_32_k3p1": (True, 64, 32, 3, 1, 1, (40, 153), 2),
     "dc2_32_32_k3p1": (True, 32, 32, 3, 1, 1, (128, 153), 1),
     "out_conv_32_32_k3": (False, 32, 32, 3, 0, 1, (50, 258), 2),
@@ -605,8 +606,10 @@ def test_conv2d_tcgen05_layers(dd, layer):
     m2.load_state_dict(mod.state_dict())
     desc = _lib.ConvDesc(B, cin, cout, hw[0], hw[1], y.shape[2], y.shape[3], k, k, 1, 1, p, p, d, d, int(t))
     assert _lib.load().dd_conv2d_tc_supported(ctypes.byref(desc), 1, 0) == 1
-    # the input gradient gathers the layer's OUTPUT channels: 16 of them (up_conv_3) are below the kernel's 32-channel K chunk
-    assert _lib.load().dd_conv2d_tc_supported(ctypes.byref(desc), 1, 1) == int(cout % 32 == 0)
+    # tensors with 16 (up_conv_3's output) or 8 / 16 channels (up_conv_4) are below the kernels' 32-channel pixels: they are
+    # zero-padded to 32 channels first, an 8-channel result is narrowed afterwards (conv_generic.cu, chan_pad32_kernel)
+    assert _lib.load().dd_conv2d_tc_supported(ctypes.byref(desc), 1, 1) == 1
+    assert _lib.load().dd_conv2d_tc_supported(ctypes.byref(desc), 1, 2) == 1
     assert _lib.load().dd_conv2d_tc_supported(ctypes.byref(desc), 0, 0) == 0          # fp32 stays on the CUDA-core parity engine
     xd = nhwc(x.detach(), dtype).requires_grad_(True)
     yd = dd.conv2d_nhwc(xd, m2, relu=True)
