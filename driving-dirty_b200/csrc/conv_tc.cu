@@ -742,9 +742,9 @@ struct C1Bars {
 // torchvision ToTensor (data_helper.py:109-114): byte -> float32, divided by 255.  The IEEE division (bit-identical to
 // x.float() / 255) is done ONCE per CTA for the 256 possible bytes into a shared-memory table; a division per pixel
 // made the raw-byte kernels instruction-bound (the c1 forward + weight gradient pair ran 1.6 ms slower per step).
-template <typename TIN> __device__ __forceinline__ float c1_ld(const TIN* p, const float* lut);
-template <> __device__ __forceinline__ float c1_ld<float>(const float* p, const float*) { return __ldg(p); }
-template <> __device__ __forceinline__ float c1_ld<uint8_t>(const uint8_t* p, const float* lut) { return lut[__ldg(p)]; }
+template <typename TIN> __device__ __forceinline__ float c1_cvt(TIN x, const float* lut);
+template <> __device__ __forceinline__ float c1_cvt<float>(float x, const float*) { return x; }
+template <> __device__ __forceinline__ float c1_cvt<uint8_t>(uint8_t x, const float* lut) { return lut[x]; }
 __device__ __forceinline__ void c1_fill_lut(float* lut) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
 }
@@ -766,19 +766,27 @@ __device__ __forceinline__ const TIN* c1_src(const TIN* __restrict__ in, int b, 
 template <bool IS_VIEWS, typename TIN>
 __device__ __forceinline__ void c1_load_row(uint8_t* __restrict__ slab, const TIN* __restrict__ in, int b, int r, int c0,
                                             int H, int Wm, int lane, const float* lut) {
+  // all 15 global loads of the lane first, conversions afterwards: with the byte -> float table look-up inside the per-pixel
+  // branch the compiler issued the loads three at a time, each group waiting for its own round trip (5 serialised global
+  // latencies per row made the raw-byte converters the limit of the fused kernel)
+  TIN raw[5][3];
   float v[5][3];
   bool ok[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const int li = lane + 32 * k, col = c0 + li;
     ok[k] = li < 130 && r >= 0 && r < H && col >= 0 && col < Wm;
+    raw[k][0] = raw[k][1] = raw[k][2] = TIN(0);
     if (ok[k]) {
       size_t cs;
       const TIN* p = c1_src<IS_VIEWS, TIN>(in, b, r, col, H, Wm, cs);
-      v[k][0] = c1_ld<TIN>(p, lut); v[k][1] = c1_ld<TIN>(p + cs, lut); v[k][2] = c1_ld<TIN>(p + 2 * cs, lut);
-    } else {
-      v[k][0] = v[k][1] = v[k][2] = 0.f;
+      raw[k][0] = __ldg(p); raw[k][1] = __ldg(p + cs); raw[k][2] = __ldg(p + 2 * cs);
     }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[k][c] = ok[k] ? c1_cvt<TIN>(raw[k][c], lut) : 0.f;
   }
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
@@ -1093,27 +1101,60 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
         umma::tc_fence_after_sync();
         if (umma::elect_one()) {
           const uint32_t slab_lo = a1_lo0 + (a % E_ARING) * (S1_SLAB >> 4);
-          const int jlo = max(s - 2, 0), jhi = min(s, rows - 1);
-          const int n = jhi - jlo + 1;                      // output rows fed: 1..3
-          const int blk = jlo - (s - 2);                    // their first kh slot in B
-          const uint32_t sl = (grb + jlo) % E_NACC2;
-          const int n1 = min(n, (int)(E_NACC2 - sl));       // rows before the accumulator ring wraps
-          const uint32_t d0 = tmem2 + sl * 32;
-          const uint32_t i0 = idesc32 + (n1 - 1) * IDESC_NSTEP, i1 = idesc32 + (n - n1 - 1) * IDESC_NSTEP;
-          const uint32_t bo0 = blk * 32, bo1 = (blk + n1) * 32;
-          const bool two = n > n1;
-          const int no = is_new ? n - 1 : n;                // rows that already hold partial sums
-          const int no1 = min(no, n1), no2 = no - no1;
 #define E_AT(t) (slab_lo + (((((t) >> 1) * 64) + ((t) & 1) * 32) >> 4))
 #define E_BT(t) (w2_lo0 + ((((((t) >> 1) * 4) + 2 * ((t) & 1)) * S1_WN) >> 4))
-          if (no1 > 0) umma::mma_bf16_lohi(d0, slab_lo, a2_hi, w2_lo0 + bo0, b_hi, idesc32 + (no1 - 1) * IDESC_NSTEP, 1u);
-          if (no2 > 0) umma::mma_bf16_lohi(tmem2, slab_lo, a2_hi, w2_lo0 + bo1, b_hi, idesc32 + (no2 - 1) * IDESC_NSTEP, 1u);
-          if (is_new)
-            umma::mma_bf16_lohi(tmem2 + ((grb + jhi) % E_NACC2) * 32, slab_lo, a2_hi, w2_lo0 + (blk + n - 1) * 32, b_hi, idesc32, 0u);
+          if (s >= 2 && is_new) {
+            // ---- interior row (62 of 66): three output rows in ring slots sl, sl+1, sl+2; straight-line issue, only the
+            //      slab and the slot change from row to row (the general form below costs ~110 uniform instructions of
+            //      descriptor arithmetic per row on the thread that is the kernel's critical path) ----
+            const uint32_t sl = (grb + s - 2) % E_NACC2;
+            const uint32_t d0 = tmem2 + sl * 32;
+            constexpr uint32_t i32 = idesc32, i64 = idesc32 + IDESC_NSTEP, i96 = idesc32 + 2 * IDESC_NSTEP;
+            if (sl <= E_NACC2 - 3) {
+              umma::mma_bf16_lohi(d0, E_AT(0), a2_hi, E_BT(0), b_hi, i64, 1u);
+              umma::mma_bf16_lohi(d0 + 64, E_AT(0), a2_hi, E_BT(0) + 64, b_hi, i32, 0u);
 #pragma unroll
-          for (int t = 1; t < 6; ++t) {
-            umma::mma_bf16_lohi(d0, E_AT(t), a2_hi, E_BT(t) + bo0, b_hi, i0, 1u);
-            if (two) umma::mma_bf16_lohi(tmem2, E_AT(t), a2_hi, E_BT(t) + bo1, b_hi, i1, 1u);
+              for (int t = 1; t < 6; ++t) umma::mma_bf16_lohi(d0, E_AT(t), a2_hi, E_BT(t), b_hi, i96, 1u);
+            } else if (sl == E_NACC2 - 2) {               // newest row wraps to slot 0
+              umma::mma_bf16_lohi(d0, E_AT(0), a2_hi, E_BT(0), b_hi, i64, 1u);
+              umma::mma_bf16_lohi(tmem2, E_AT(0), a2_hi, E_BT(0) + 64, b_hi, i32, 0u);
+#pragma unroll
+              for (int t = 1; t < 6; ++t) {
+                umma::mma_bf16_lohi(d0, E_AT(t), a2_hi, E_BT(t), b_hi, i64, 1u);
+                umma::mma_bf16_lohi(tmem2, E_AT(t), a2_hi, E_BT(t) + 64, b_hi, i32, 1u);
+              }
+            } else {                                      // slots 11, 0, 1
+              umma::mma_bf16_lohi(d0, E_AT(0), a2_hi, E_BT(0), b_hi, i32, 1u);
+              umma::mma_bf16_lohi(tmem2, E_AT(0), a2_hi, E_BT(0) + 32, b_hi, i32, 1u);
+              umma::mma_bf16_lohi(tmem2 + 32, E_AT(0), a2_hi, E_BT(0) + 64, b_hi, i32, 0u);
+#pragma unroll
+              for (int t = 1; t < 6; ++t) {
+                umma::mma_bf16_lohi(d0, E_AT(t), a2_hi, E_BT(t), b_hi, i32, 1u);
+                umma::mma_bf16_lohi(tmem2, E_AT(t), a2_hi, E_BT(t) + 32, b_hi, i64, 1u);
+              }
+            }
+          } else {
+            // ---- first / last two a1 rows of an item (or a very short item): general form ----
+            const int jlo = max(s - 2, 0), jhi = min(s, rows - 1);
+            const int n = jhi - jlo + 1;                      // output rows fed: 1..3
+            const int blk = jlo - (s - 2);                    // their first kh slot in B
+            const uint32_t sl = (grb + jlo) % E_NACC2;
+            const int n1 = min(n, (int)(E_NACC2 - sl));       // rows before the accumulator ring wraps
+            const uint32_t d0 = tmem2 + sl * 32;
+            const uint32_t i0 = idesc32 + (n1 - 1) * IDESC_NSTEP, i1 = idesc32 + (n - n1 - 1) * IDESC_NSTEP;
+            const uint32_t bo0 = blk * 32, bo1 = (blk + n1) * 32;
+            const bool two = n > n1;
+            const int no = is_new ? n - 1 : n;                // rows that already hold partial sums
+            const int no1 = min(no, n1), no2 = no - no1;
+            if (no1 > 0) umma::mma_bf16_lohi(d0, slab_lo, a2_hi, w2_lo0 + bo0, b_hi, idesc32 + (no1 - 1) * IDESC_NSTEP, 1u);
+            if (no2 > 0) umma::mma_bf16_lohi(tmem2, slab_lo, a2_hi, w2_lo0 + bo1, b_hi, idesc32 + (no2 - 1) * IDESC_NSTEP, 1u);
+            if (is_new)
+              umma::mma_bf16_lohi(tmem2 + ((grb + jhi) % E_NACC2) * 32, slab_lo, a2_hi, w2_lo0 + (blk + n - 1) * 32, b_hi, idesc32, 0u);
+#pragma unroll
+            for (int t = 1; t < 6; ++t) {
+              umma::mma_bf16_lohi(d0, E_AT(t), a2_hi, E_BT(t) + bo0, b_hi, i0, 1u);
+              if (two) umma::mma_bf16_lohi(tmem2, E_AT(t), a2_hi, E_BT(t) + bo1, b_hi, i1, 1u);
+            }
           }
 #undef E_AT
 #undef E_BT

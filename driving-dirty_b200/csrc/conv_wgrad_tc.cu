@@ -303,9 +303,11 @@ static_assert(C1_SMEM <= 227 * 1024, "shared memory");
 // torchvision ToTensor (data_helper.py:109-114): byte -> float32, divided by 255.  The IEEE division (bit-identical to
 // x.float() / 255) is done ONCE per CTA for the 256 possible bytes into a shared-memory table; a division per pixel
 // made the raw-byte kernels instruction-bound (the c1 forward + weight gradient pair ran 1.6 ms slower per step).
-template <typename TIN> __device__ __forceinline__ float c1_ld(const TIN* p, const float* lut);
-template <> __device__ __forceinline__ float c1_ld<float>(const float* p, const float*) { return __ldg(p); }
-template <> __device__ __forceinline__ float c1_ld<uint8_t>(const uint8_t* p, const float* lut) { return lut[__ldg(p)]; }
+// byte -> float through the table AFTER the prefetch distance: a look-up at load time would make every prefetched global
+// load wait for its own round trip (the raw-byte kernel ran 0.37 ms against 0.25 for fp32 views)
+template <typename TIN> __device__ __forceinline__ float c1_cvt(TIN x, const float* lut);
+template <> __device__ __forceinline__ float c1_cvt<float>(float x, const float*) { return x; }
+template <> __device__ __forceinline__ float c1_cvt<uint8_t>(uint8_t x, const float* lut) { return lut[x]; }
 __device__ __forceinline__ void c1_fill_lut(float* lut) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
 }
@@ -374,23 +376,23 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_wgrad_ring_kernel(const
       c.it += gridDim.x;
       open_item(c);
     };
-    auto load_rows = [&](const Cur& c, float (&v)[C1_RB][3], float (&e)[C1_RB][3]) {
+    auto load_rows = [&](const Cur& c, TIN (&v)[C1_RB][3], TIN (&e)[C1_RB][3]) {      // raw values; 0 where there is no pixel
 #pragma unroll
       for (int r = 0; r < C1_RB; ++r) {
         const int row = c.xr0 + r;
         const bool row_ok = row >= 0 && row < H;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          v[r][ch] = (row_ok && c.cok) ? c1_ld<TIN>(in + c.coff + ch * cstride + (size_t)row * Wv, s_lut) : 0.f;
-          e[r][ch] = (has_edge && row_ok && c.eok) ? c1_ld<TIN>(in + c.eoff + ch * cstride + (size_t)row * Wv, s_lut) : 0.f;
+          v[r][ch] = (row_ok && c.cok) ? __ldg(in + c.coff + ch * cstride + (size_t)row * Wv) : TIN(0);
+          e[r][ch] = (has_edge && row_ok && c.eok) ? __ldg(in + c.eoff + ch * cstride + (size_t)row * Wv) : TIN(0);
         }
       }
     };
     Cur cur;
     cur.it = blockIdx.x;
     open_item(cur);
-    float v[C1_RB][3], e[C1_RB][3], vn[C1_RB][3], en[C1_RB][3];
-    if (cur.valid) load_rows(cur, v, e);
+    TIN rv[C1_RB][3], re[C1_RB][3], vn[C1_RB][3], en[C1_RB][3];
+    if (cur.valid) load_rows(cur, rv, re);
     uint32_t g = 0;
     while (cur.valid) {
       Cur nxt = cur;
@@ -398,6 +400,11 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_wgrad_ring_kernel(const
       if (nxt.valid) load_rows(nxt, vn, en);
       const uint32_t s = g % C1_NS;
       umma::mbar_wait(&bars->empty[s], ((g / C1_NS) & 1) ^ 1);
+      float v[C1_RB][3], e[C1_RB][3];
+#pragma unroll
+      for (int r = 0; r < C1_RB; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { v[r][c] = c1_cvt<TIN>(rv[r][c], s_lut); e[r][c] = c1_cvt<TIN>(re[r][c], s_lut); }
 #pragma unroll
       for (int r = 0; r < C1_RB; ++r) {
         float lf[3], rt[3];
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_wgrad_ring_kernel(const
 #pragma unroll
       for (int r = 0; r < C1_RB; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { v[r][c] = vn[r][c]; e[r][c] = en[r][c]; }
+        for (int c = 0; c < 3; ++c) { rv[r][c] = vn[r][c]; re[r][c] = en[r][c]; }
       cur = nxt;
     }
   } else if (warp == 5) {

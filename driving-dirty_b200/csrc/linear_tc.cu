@@ -3,8 +3,9 @@
 //   Encoder.fc1.fc1  Linear(940,032 -> hidden)   components.py:26,105
 //   roadmap head     Linear(latent -> 640,000)   roadmap_bce_v2.py:50,75
 //   Decoder.fc2.fc1  Linear(hidden -> 1,253,376) components.py:69
-// All three passes are HBM-bound (the weight, or its gradient, crosses HBM exactly once per 32 batch
-// rows); the batch (<= 32 rows per launch) is the narrow MMA dimension.
+// All three passes are HBM-bound (the weight, or its gradient, crosses HBM exactly once per pass over
+// the batch); the batch is the narrow MMA dimension: 32 rows per pass in the training step (forward,
+// dgrad, wgrad), up to 256 rows per pass in the forward (inference batches; SCfg below).
 //
 //   fwd   y[b][n]  = sum_k x[b][k] W[n][k]     D[128 n x 32 b]:  A = W tile, K-major (SWIZZLE_128B);
 //                                              B = x tile, K-major

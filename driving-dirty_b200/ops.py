@@ -135,12 +135,13 @@ class EncoderConvStack(torch.autograd.Function):
         _require_cuda(inp, w1, w2, w3)
         inp = _c(inp)
         inference = not any(ctx.needs_input_grad)
-        fused_front = inference and act_dtype == torch.bfloat16 and impl != _lib.IMPL_SIMT
-        if inp.dtype == torch.uint8 and not fused_front:
-            # raw camera bytes: ToTensor's /255 as a pass of its own (0.04 ms for 32 scenes).  The c1 kernels can also read
-            # bytes directly (DD_IN_U8, bit-identical, tested), but their byte-granular loads keep too few bytes in flight:
-            # +0.26 ms per step measured (profiles/r2_kernel_times.txt), so the training path converts first.  The fused
-            # inference front is not bound by its converter warps: it reads the bytes itself (+0.03 ms against 0.08 for the pass)
+        tensor_core = act_dtype == torch.bfloat16 and impl != _lib.IMPL_SIMT
+        fused_front = inference and tensor_core
+        if inp.dtype == torch.uint8 and not tensor_core:
+            # raw camera bytes on the fp32 parity path: ToTensor's /255 as a pass of its own (dd_u8_to_f32).  The tensor-core
+            # kernels (c1 forward, c1 weight gradient, the fused inference front) read the bytes themselves (DD_IN_U8,
+            # bit-identical, tested): their converter warps issue all loads of a row before the first table look-up, so
+            # bytes cost them nothing (0.29 / 0.25 ms either way, profiles/r2_kernel_times.txt) and the pass (0.07 ms, 200 MB) goes
             inp = bytes_to_float(inp)
         is_views = inp.dim() == 5
         if is_views:
