@@ -930,7 +930,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __
 // The first activation (963 MB per 32 scenes as bf16) never touches HBM: a CTA walks a strip of 126 output
 // pixels down 64 rows; per row
 //   converter warps   views / mosaic row (fp32 or raw bytes) -> [130 px][8 ch] bf16 plane      (as conv_c1_tc_kernel)
-//   two MMA warps     c1: 6 MMAs (M=128, N=32) over three planes -> TMEM;  c2: row-scatter MMAs (as the s1 kernel) over
+//   two MMA warps     c1: row-scatter MMAs (N = 96, two taps per K = 16) over the planes -> TMEM;  c2: row-scatter MMAs over
 //                     the a1 slab the first epilogue wrote.  Two issuing threads because every mbarrier wait and
 //                     tcgen05.commit costs its thread 100-200 cycles: one thread doing both batches left the pipe idle
 //                     60 % of the time (0.76 ms per 32 scenes; two issuers + 8-warp epilogues: 0.50)
@@ -940,8 +940,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv_c1_tc_kernel(const TIN* __
 //   epilogue 2        TMEM -> bias + ReLU -> bf16 -> a2 in HBM (bit-identical to the two-kernel path: a1 is rounded to
 //                     bf16 at the same point, the MMAs see the same operands in the same order)
 // Halo recompute: 128 a1 pixels per 126 outputs, 66 a1 rows per 64.  Hand-shakes: the MMA warp publishes ONE commit
-// per c1 batch (c1_done: accumulator full + oldest plane free) and ONE per c2 batch (c2_done: output row j-2 complete +
-// a1 slab free); ring indices are global row counters, two no-op commits per item keep c1_done in step with the planes.
+// per c1 batch (c1_done: a1 row v-2 complete + plane v free) and ONE per c2 batch (c2_done: output row j-2 complete +
+// a1 slab free); ring indices are global plane / row counters.
 // ================================================================================================
 constexpr int E_STRIP = 126;
 constexpr int E_ROWS = 64;
@@ -955,7 +955,8 @@ constexpr int E_THREADS = 32 * (E_NCONV + 2 + E_EPI1 + E_EPI2);
 constexpr int E_VRING = 12;                          // view planes
 constexpr int E_VS = 17 * 128;                       // [130 px][16 B]
 constexpr int E_ARING = 8;                           // a1 slabs (S1_SLAB bytes each)
-constexpr int E_NACC1 = 4, E_NACC2 = 12;             // TMEM: 4 x 32 columns for c1, 12 x 32 for the c2 ring
+constexpr int E_NACC1 = 8, E_NACC2 = 8;              // TMEM: two rings of 8 x 32 columns (both layers scatter into three slots)
+constexpr int E_W1N = 96 * 16;                       // c1 B operand: bytes per K chunk block [3 kh slots x 32 co][8 ch]
 constexpr int E_DONE = 16;
 constexpr int E_OFF_W1 = W_BYTES;
 constexpr int E_OFF_A1 = W_BYTES + 6 * 1024;
@@ -989,16 +990,17 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
   const int hsegs = (H + E_ROWS - 1) / E_ROWS;
   const int items = B * wtiles * hsegs;
 
-  // c2 weights: [kw][cg][slot = 2 - kh][co][8 ci] (the s1 kernel's B operand); c1 weights: [kh][pair][kchunk][co][8 ch]
+  // c2 weights: [kw][cg][slot = 2 - kh][co][8 ci] (the s1 kernel's B operand); c1 weights: [pair][kchunk][slot = 2 - kh][co][8 ch]
   for (int i = tid; i < 9 * C * C; i += E_THREADS) {
     const int ci = i & 31, co = (i >> 5) & 31, tap = i >> 10;
     const int kh = tap / 3, kw = tap - 3 * kh;
     *reinterpret_cast<__nv_bfloat16*>(s_w2 + (kw * 4 + (ci >> 3)) * S1_WN + ((2 - kh) * 32 + co) * 16 + (ci & 7) * 2) =
         __float2bfloat16_rn(w2_oihw[(co * C + ci) * 9 + tap]);
   }
-  for (int i = tid; i < 6 * 1024 / 2; i += E_THREADS) {
-    const int ch = i & 7, co = (i >> 3) & 31, kc = (i >> 8) & 1, pr = (i >> 9) & 1, kh = i >> 10;
-    const int kw = 2 * pr + kc;
+  for (int i = tid; i < 6 * 1024 / 2; i += E_THREADS) {           // [pair][kchunk][slot = 2 - kh][co][8 ch]
+    const int ch = i & 7, co = (i >> 3) & 31;
+    const int slot = (i >> 8) % 3, kc = ((i >> 8) / 3) & 1, pr = (i >> 8) / 6;
+    const int kh = 2 - slot, kw = 2 * pr + kc;
     const float v = (kw < 3 && ch < 3) ? w1_oihw[((co * 3 + ch) * 3 + kh) * 3 + kw] : 0.f;
     reinterpret_cast<__nv_bfloat16*>(s_w1)[i] = __float2bfloat16_rn(v);
   }
@@ -1043,35 +1045,49 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
       gvb += rows + 4;
     }
   } else if (warp == E_MMA_WARP) {
-    // =========================== c1 issuer: a1 row u of the item from planes u, u+1, u+2 ============
+    // =========================== c1 issuer: plane v feeds a1 rows v-2 (kh = 2), v-1 (kh = 1), v (kh = 0) ==========
+    // Row scatter here too: ONE plane is read by two MMAs of N = 96 (K = 16 = two horizontal taps) instead of six MMAs of
+    // N = 32 per a1 row re-reading three planes (112 instead of 240 cycles of the shared tensor pipe per row).  Per a1 row
+    // the accumulation order stays kh = 0, 1, 2 with the pairs inside: the same bits as conv_c1_tc_kernel.
     constexpr uint32_t idesc32 = umma::make_idesc_bf16(TILE_M, 32, false, false);
+    constexpr uint32_t IDESC_NSTEP = (32u >> 3) << 17;
     constexpr uint32_t ab_hi = umma::desc_hi(128);                            // A and B: SWIZZLE_NONE, SBO = 128
-    const uint32_t v_lo0 = umma::desc_lo(umma::smem_u32(s_v), 16);            // second K chunk = next pixel
-    const uint32_t w1_lo0 = umma::desc_lo(umma::smem_u32(s_w1), 512);
-    uint32_t gvb = 0, gab = 0, v_waited = 0;
+    const uint32_t v_lo0 = umma::desc_lo(umma::smem_u32(s_v), 16);            // A: second K chunk = next pixel
+    const uint32_t w1_lo0 = umma::desc_lo(umma::smem_u32(s_w1), E_W1N);       // B: LBO = K chunk block
+    constexpr uint32_t W1_PAIR = (2 * E_W1N) >> 4;                            // second tap pair
+    uint32_t gvb = 0, gab = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int hs = (it / wtiles) % hsegs;
       const int rows = min(E_ROWS, H - hs * E_ROWS);
       const int na = rows + 2;
-      for (int u = 0; u < na; ++u) {
-        for (; v_waited < gvb + u + 3; ++v_waited) umma::mbar_wait(&bars->v_full[v_waited % E_VRING], (v_waited / E_VRING) & 1);
-        const uint32_t a = gab + u, buf = a % E_NACC1;
-        umma::mbar_wait(&bars->acc1_empty[buf], ((a / E_NACC1) & 1) ^ 1);
+      for (int v = 0; v < na + 2; ++v) {
+        const uint32_t gv = gvb + v;
+        umma::mbar_wait(&bars->v_full[gv % E_VRING], (gv / E_VRING) & 1);
+        const bool is_new = v < na;                         // a1 row v receives its first contribution
+        if (is_new) {
+          const uint32_t a = gab + v;
+          umma::mbar_wait(&bars->acc1_empty[a % E_NACC1], ((a / E_NACC1) & 1) ^ 1);
+        }
         umma::tc_fence_after_sync();
         if (umma::elect_one()) {
-#pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t pl = v_lo0 + ((gvb + u + kh) % E_VRING) * (E_VS >> 4);
-#pragma unroll
-            for (int pr = 0; pr < 2; ++pr)
-              umma::mma_bf16_lohi(tmem + buf * 32, pl + 2 * pr, ab_hi, w1_lo0 + ((kh * 2 + pr) * 1024 >> 4), ab_hi, idesc32,
-                                  (kh | pr) ? 1u : 0u);
-          }
-          umma::mma_commit(&bars->c1_done[(gvb + u) % E_DONE]);
-          if (u == na - 1) {                               // planes na, na+1 of the item have no batch of their own
-            umma::mma_commit(&bars->c1_done[(gvb + na) % E_DONE]);
-            umma::mma_commit(&bars->c1_done[(gvb + na + 1) % E_DONE]);
-          }
+          const uint32_t pl = v_lo0 + (gv % E_VRING) * (E_VS >> 4);
+          const int jlo = max(v - 2, 0), jhi = min(v, na - 1);
+          const int n = jhi - jlo + 1;                      // a1 rows fed: 1..3
+          const int blk = jlo - (v - 2);                    // their first kh slot in B
+          const uint32_t sl = (gab + jlo) % E_NACC1;
+          const int n1 = min(n, (int)(E_NACC1 - sl));       // rows before the accumulator ring wraps
+          const uint32_t d0 = tmem + sl * 32;
+          const uint32_t bo0 = blk * 32, bo1 = (blk + n1) * 32;
+          const int no = is_new ? n - 1 : n;                // rows that already hold partial sums
+          const int no1 = min(no, n1), no2 = no - no1;
+          // pair 0: accumulate into the older rows, overwrite the newest; pair 1: accumulate into all
+          if (no1 > 0) umma::mma_bf16_lohi(d0, pl, ab_hi, w1_lo0 + bo0, ab_hi, idesc32 + (no1 - 1) * IDESC_NSTEP, 1u);
+          if (no2 > 0) umma::mma_bf16_lohi(tmem, pl, ab_hi, w1_lo0 + bo1, ab_hi, idesc32 + (no2 - 1) * IDESC_NSTEP, 1u);
+          if (is_new)
+            umma::mma_bf16_lohi(tmem + ((gab + jhi) % E_NACC1) * 32, pl, ab_hi, w1_lo0 + (blk + n - 1) * 32, ab_hi, idesc32, 0u);
+          umma::mma_bf16_lohi(d0, pl + 2, ab_hi, w1_lo0 + W1_PAIR + bo0, ab_hi, idesc32 + (n1 - 1) * IDESC_NSTEP, 1u);
+          if (n > n1) umma::mma_bf16_lohi(tmem, pl + 2, ab_hi, w1_lo0 + W1_PAIR + bo1, ab_hi, idesc32 + (n - n1 - 1) * IDESC_NSTEP, 1u);
+          umma::mma_commit(&bars->c1_done[gv % E_DONE]);   // plane gv is free; a1 row v-2 is complete
         }
         __syncwarp();
       }
@@ -1123,7 +1139,7 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
                 umma::mma_bf16_lohi(d0, E_AT(t), a2_hi, E_BT(t), b_hi, i64, 1u);
                 umma::mma_bf16_lohi(tmem2, E_AT(t), a2_hi, E_BT(t) + 64, b_hi, i32, 1u);
               }
-            } else {                                      // slots 11, 0, 1
+            } else {                                      // last slot, then slots 0 and 1
               umma::mma_bf16_lohi(d0, E_AT(0), a2_hi, E_BT(0), b_hi, i32, 1u);
               umma::mma_bf16_lohi(tmem2, E_AT(0), a2_hi, E_BT(0) + 32, b_hi, i32, 1u);
               umma::mma_bf16_lohi(tmem2 + 32, E_AT(0), a2_hi, E_BT(0) + 64, b_hi, i32, 0u);
@@ -1182,7 +1198,7 @@ __global__ void __maxnreg__(80) enc_c1c2_fused_kernel(const TIN* __restrict__ in
       const int col = wt * E_STRIP - 1 + m;
       const bool col_ok = col >= 0 && col < Wm;
       for (int t = (int)((gab ^ half) & 1); t < rows + 2; t += 2) {
-        const uint32_t a = gab + t, buf = a % E_NACC1, dv = gvb + t;
+        const uint32_t a = gab + t, buf = a % E_NACC1, dv = gvb + t + 2;      // complete after plane t+2's batch
         umma::mbar_wait(&bars->c1_done[dv % E_DONE], (dv / E_DONE) & 1);
         umma::tc_fence_after_sync();
         uint32_t r[32];
