@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/tests.log
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-for k in ${KGROUPS:-tcgen05 stitch conv3x3_fwd_simt dgrad_wgrad conv_c1 pool4 layout linear bce_threat binarise threat_score}; do
+for k in ${KGROUPS:-tcgen05 c1c2_fused stitch conv3x3_fwd_simt dgrad_wgrad conv_c1 conv2d pool4 layout linear bce_threat binarise threat_score ats guard}; do
   echo "=== $k" >> gpurun_out/tests.log
   timeout 240 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "$k" -x 2>&1 | tail -25 >> gpurun_out/tests.log
 done
